@@ -1,0 +1,224 @@
+// emu.hpp -- TEST INFRASTRUCTURE ONLY: a tiny cooperative-fiber SIMT emulator.
+//
+// It lets the kernel sources under trpx_b200/csrc/ be compiled with plain g++ (-DTRPX_EMU) and run
+// on the CPU so that `pytest -m "not gpu"` can check their index arithmetic, scans, look-back and
+// bit packing against the oracle.  One ucontext fiber per CUDA thread; the blocks of a grid run one
+// after another (so a look-back never has to wait), barriers and warp collectives are rendez-vous
+// points between fibers.  It is never part of libtrpx_b200.so.
+#pragma once
+
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <ucontext.h>
+
+#include <functional>
+#include <vector>
+
+namespace emu {
+
+typedef int cudaError_t;
+typedef void* cudaStream_t;
+enum { cudaSuccess = 0 };
+
+struct alignas(16) uint4 { uint32_t x, y, z, w; };
+inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+
+struct ThreadCtx { uint32_t tid, bid, block_dim, grid_dim; };
+
+struct Fiber {
+    ucontext_t ctx;
+    char* stack = nullptr;
+    bool done = false;
+    ThreadCtx tc{};
+};
+
+struct State {
+    std::vector<Fiber> fibers;
+    ucontext_t sched;
+    int current = -1;
+    uint32_t bar_count = 0, bar_gen = 0;
+    std::vector<uint32_t> wbar_count, wbar_gen;
+    std::vector<uint64_t> xch;            // 32 slots per warp
+    unsigned char* smem = nullptr;
+    const std::function<void()>* body = nullptr;
+    uint64_t yields_without_progress = 0;
+};
+
+inline State& S() { static State s; return s; }
+inline ThreadCtx& cur() { return S().fibers[S().current].tc; }
+inline unsigned char* dyn_smem() { return S().smem; }
+
+inline void yield()
+{
+    State& s = S();
+    if (++s.yields_without_progress > (1ull << 28)) { fprintf(stderr, "emu: livelock\n"); abort(); }
+    swapcontext(&s.fibers[s.current].ctx, &s.sched);
+}
+inline void progress() { S().yields_without_progress = 0; }
+inline void trap() { fprintf(stderr, "emu: trap() in block %u thread %u\n", cur().bid, cur().tid); abort(); }
+
+inline void sync_block()
+{
+    State& s = S();
+    uint32_t gen = s.bar_gen;
+    if (++s.bar_count == cur().block_dim) { s.bar_count = 0; ++s.bar_gen; progress(); }
+    else while (s.bar_gen == gen) yield();
+}
+
+inline void sync_warp()
+{
+    State& s = S();
+    uint32_t w = cur().tid >> 5;
+    uint32_t lanes = cur().block_dim - w * 32 < 32 ? cur().block_dim - w * 32 : 32;
+    uint32_t gen = s.wbar_gen[w];
+    if (++s.wbar_count[w] == lanes) { s.wbar_count[w] = 0; ++s.wbar_gen[w]; progress(); }
+    else while (s.wbar_gen[w] == gen) yield();
+}
+
+inline uint64_t shfl(uint64_t v, int src)
+{
+    State& s = S();
+    uint32_t t = cur().tid, w = t >> 5;
+    s.xch[w * 32 + (t & 31)] = v;
+    sync_warp();
+    uint64_t r = s.xch[w * 32 + (src & 31)];
+    sync_warp();
+    return r;
+}
+inline uint64_t shfl_up(uint64_t v, int d)
+{
+    int l = (int)(cur().tid & 31);
+    return shfl(v, l - d >= 0 ? l - d : l);
+}
+inline uint64_t shfl_down(uint64_t v, int d)
+{
+    int l = (int)(cur().tid & 31);
+    return shfl(v, l + d <= 31 ? l + d : l);
+}
+inline uint32_t ballot(bool p)
+{
+    State& s = S();
+    uint32_t t = cur().tid, w = t >> 5;
+    s.xch[w * 32 + (t & 31)] = p ? 1 : 0;
+    sync_warp();
+    uint32_t m = 0;
+    uint32_t lanes = cur().block_dim - w * 32 < 32 ? cur().block_dim - w * 32 : 32;
+    for (uint32_t i = 0; i < lanes; ++i) m |= (uint32_t)s.xch[w * 32 + i] << i;
+    sync_warp();
+    return m;
+}
+inline uint32_t warp_reduce(uint32_t v, int op)
+{
+    State& s = S();
+    uint32_t t = cur().tid, w = t >> 5;
+    s.xch[w * 32 + (t & 31)] = v;
+    sync_warp();
+    uint32_t lanes = cur().block_dim - w * 32 < 32 ? cur().block_dim - w * 32 : 32;
+    uint32_t r = op == 0 ? 0 : 0;
+    for (uint32_t i = 0; i < lanes; ++i) {
+        uint32_t x = (uint32_t)s.xch[w * 32 + i];
+        r = op == 0 ? (x > r ? x : r) : op == 1 ? (r | x) : (r + x);
+    }
+    sync_warp();
+    return r;
+}
+
+// mbarrier emulation in the barrier's own 8 bytes
+struct MBar { uint8_t expected, arrived, phase, pad; int32_t tx; };
+static_assert(sizeof(MBar) == 8, "emulated mbarrier must fit the 8-byte hardware object");
+inline void mbar_check(MBar* b)
+{
+    if (b->arrived >= b->expected && b->tx == 0) { b->phase ^= 1; b->arrived = 0; progress(); }
+}
+inline void mbar_init(unsigned long long* bar, uint32_t count)
+{
+    MBar* b = (MBar*)bar;
+    memset(b, 0, sizeof(MBar));
+    b->expected = (uint8_t)count;
+}
+inline void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes)
+{
+    MBar* b = (MBar*)bar;
+    b->tx += (int32_t)bytes;
+    b->arrived++;
+    mbar_check(b);
+}
+inline void mbar_wait(unsigned long long* bar, uint32_t parity)
+{
+    MBar* b = (MBar*)bar;
+    while ((uint32_t)b->phase == (parity & 1)) yield();   // phase flips when the awaited phase completes
+}
+inline void bulk_g2s(void* d, const void* s, uint32_t bytes, unsigned long long* bar)
+{
+    if (((uintptr_t)d | (uintptr_t)s | bytes) & 15) { fprintf(stderr, "emu: misaligned bulk_g2s\n"); abort(); }
+    memcpy(d, s, bytes);
+    MBar* b = (MBar*)bar;
+    b->tx -= (int32_t)bytes;
+    mbar_check(b);
+}
+inline void bulk_s2g(void* d, const void* s, uint32_t bytes)
+{
+    if (((uintptr_t)d | (uintptr_t)s | bytes) & 15) { fprintf(stderr, "emu: misaligned bulk_s2g\n"); abort(); }
+    memcpy(d, s, bytes);
+}
+
+inline void fiber_entry()
+{
+    State& s = S();
+    (*s.body)();
+    s.fibers[s.current].done = true;
+    progress();
+    swapcontext(&s.fibers[s.current].ctx, &s.sched);
+}
+
+inline void run_grid(uint32_t grid, uint32_t block, size_t smem_bytes, const std::function<void()>& body)
+{
+    State& s = S();
+    const size_t STACK = 256 * 1024;
+    static unsigned char* smem_buf = nullptr;
+    if (!smem_buf) smem_buf = (unsigned char*)aligned_alloc(1024, 256 * 1024);
+    if (smem_bytes > 232448) { fprintf(stderr, "emu: %zu bytes of dynamic smem exceed 227 KB\n", smem_bytes); abort(); }
+    s.smem = smem_buf;
+    s.body = &body;
+    if (s.fibers.size() < block) {
+        size_t old = s.fibers.size();
+        s.fibers.resize(block);
+        for (size_t i = old; i < block; ++i) s.fibers[i].stack = (char*)malloc(STACK);
+    }
+    uint32_t nw = (block + 31) / 32;
+    for (uint32_t b = 0; b < grid; ++b) {
+        s.bar_count = 0; s.bar_gen = 0;
+        s.wbar_count.assign(nw, 0); s.wbar_gen.assign(nw, 0);
+        s.xch.assign((size_t)nw * 32, 0);
+        memset(smem_buf, 0xA5, smem_bytes);              // uninitialised shared memory is garbage
+        for (uint32_t t = 0; t < block; ++t) {
+            Fiber& f = s.fibers[t];
+            f.done = false;
+            f.tc = ThreadCtx{t, b, block, grid};
+            getcontext(&f.ctx);
+            f.ctx.uc_stack.ss_sp = f.stack;
+            f.ctx.uc_stack.ss_size = STACK;
+            f.ctx.uc_link = nullptr;
+            makecontext(&f.ctx, (void (*)())fiber_entry, 0);
+        }
+        uint32_t alive = block;
+        s.yields_without_progress = 0;
+        while (alive) {
+            for (uint32_t t = 0; t < block; ++t) {
+                Fiber& f = s.fibers[t];
+                if (f.done) continue;
+                s.current = (int)t;
+                swapcontext(&s.sched, &f.ctx);
+                if (f.done) --alive;
+            }
+        }
+        s.current = -1;
+    }
+}
+
+// minimal runtime shims used by the launch sequences in codec_launch.cuh
+inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
+
+}  // namespace emu

@@ -1,0 +1,29 @@
+// emu_lib.cpp -- TEST INFRASTRUCTURE ONLY: the kernel sources compiled for the host (-DTRPX_EMU) and
+// driven through the same launch sequences (codec_launch.cuh) the product uses, with host memory
+// standing in for device memory.  Built by tests/emu_build.py into tests/emu/libtrpx_emu.so.
+#include <stdlib.h>
+#include <string.h>
+
+#include "codec_launch.cuh"
+
+using namespace trpx;
+
+extern "C" {
+
+int emu_encode(const void* px, int dtype, size_t n, size_t frames, unsigned block, uint8_t* out,
+               size_t cap, uint64_t* frame_ends, uint32_t* prolix_bits, uint32_t* status,
+               unsigned dbg_incl_stride, int* used_fast)
+{
+    EncPlan pl = enc_plan(dtype, px, n, frames, block);
+    if (!pl.ok) return 1;
+    if (used_fast) *used_fast = pl.fast ? 1 : 0;
+    void* scratch = malloc(pl.scratch_bytes);
+    memset(scratch, 0x5A, pl.scratch_bytes);
+    Launcher L{nullptr, 1, nullptr, cudaSuccess};
+    encode_async(L, dtype, px, n, frames, block, out, cap, (u64*)frame_ends, prolix_bits, status, scratch, pl,
+                 3, dbg_incl_stride);
+    free(scratch);
+    return 0;
+}
+
+}

@@ -1,0 +1,275 @@
+// simt.cuh -- the thin layer the kernels are written against.
+//
+// Product build (nvcc, sm_100a): every wrapper below is the CUDA intrinsic or the inline PTX it
+// names (mbarrier, cp.async.bulk = TMA bulk copies, relaxed/acquire global accesses).
+//
+// TEST build (-DTRPX_EMU, plain g++): the same kernel sources are compiled for the host and run by
+// tests/emu/emu.hpp, a cooperative-fiber SIMT emulator (one fiber per CUDA thread, blocks run one
+// after another).  That build exists only so `pytest -m "not gpu"` can check the kernels' index
+// arithmetic against the oracle without a GPU; it is never linked into libtrpx_b200.so and is not a
+// fallback: the product library has no host execution path.
+#pragma once
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef TRPX_EMU
+#include "emu.hpp"
+#else
+#include <cuda_runtime.h>
+#endif
+
+namespace trpx {
+
+typedef unsigned long long u64;
+typedef long long i64;
+typedef unsigned int u32;
+
+#ifndef TRPX_EMU
+// ----------------------------------------------------------------------------- CUDA backend
+#define TRPX_DEVICE __device__ __forceinline__
+#define TRPX_HD __host__ __device__ __forceinline__
+#define TRPX_KERNEL __global__
+#define TRPX_SHARED __shared__
+#define TRPX_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+#define TRPX_LAUNCH_BOUNDS(t, b) __launch_bounds__(t, b)
+
+TRPX_DEVICE u32 tid() { return threadIdx.x; }
+TRPX_DEVICE u32 bid() { return blockIdx.x; }
+TRPX_DEVICE u32 nthreads() { return blockDim.x; }
+TRPX_DEVICE u32 nblocks() { return gridDim.x; }
+TRPX_DEVICE void sync_block() { __syncthreads(); }
+TRPX_DEVICE void sync_warp() { __syncwarp(); }
+TRPX_DEVICE void spin_hint() { __nanosleep(32); }
+TRPX_DEVICE void trap() { __trap(); }
+
+TRPX_DEVICE u32 shfl(u32 v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+TRPX_DEVICE u64 shfl(u64 v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+TRPX_DEVICE u32 shfl_up(u32 v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+TRPX_DEVICE u64 shfl_up(u64 v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+TRPX_DEVICE u32 shfl_down(u32 v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+TRPX_DEVICE u32 shfl_xor(u32 v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+TRPX_DEVICE u32 ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+TRPX_DEVICE bool all_lanes(bool p) { return __all_sync(0xffffffffu, p); }
+TRPX_DEVICE bool any_lane(bool p) { return __any_sync(0xffffffffu, p); }
+TRPX_DEVICE u32 warp_max(u32 v) { return __reduce_max_sync(0xffffffffu, v); }
+TRPX_DEVICE u32 warp_or(u32 v) { return __reduce_or_sync(0xffffffffu, v); }
+TRPX_DEVICE u32 warp_add(u32 v) { return __reduce_add_sync(0xffffffffu, v); }
+
+TRPX_DEVICE int clz32(u32 x) { return __clz((int)x); }
+TRPX_DEVICE int clz64(u64 x) { return __clzll((long long)x); }
+TRPX_DEVICE int ffs32(u32 x) { return __ffs((int)x); }
+TRPX_DEVICE int ffs64(u64 x) { return __ffsll((long long)x); }
+TRPX_DEVICE int popc32(u32 x) { return __popc(x); }
+TRPX_DEVICE u32 funnel_r(u32 lo, u32 hi, u32 sh) { return __funnelshift_r(lo, hi, sh); }   // sh & 31
+TRPX_DEVICE u32 funnel_l(u32 lo, u32 hi, u32 sh) { return __funnelshift_l(lo, hi, sh); }   // (hi:lo << sh) >> 32
+TRPX_DEVICE u32 vabs2(u32 x) { return __vabs2(x); }   // |.| per signed 16-bit half (wraps for -32768)
+TRPX_DEVICE u32 vabs4(u32 x) { return __vabs4(x); }   // |.| per signed byte
+
+TRPX_DEVICE u32 atomic_add(u32* p, u32 v) { return atomicAdd(p, v); }
+TRPX_DEVICE u64 atomic_add(u64* p, u64 v) { return atomicAdd(p, v); }
+TRPX_DEVICE u32 atomic_or(u32* p, u32 v) { return atomicOr(p, v); }
+TRPX_DEVICE u32 atomic_max(u32* p, u32 v) { return atomicMax(p, v); }
+
+// 64-bit descriptor words: value and status travel in ONE word, so relaxed accesses suffice
+TRPX_DEVICE u64 ld_relaxed(const u64* p)
+{
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+TRPX_DEVICE void st_relaxed(u64* p, u64 v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+TRPX_DEVICE u32 ld_relaxed(const u32* p)
+{
+    u32 v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// streaming (read-once / write-once) global accesses: keep them out of L1
+TRPX_DEVICE u32 ld_stream(const u32* p) { return __ldcs(p); }
+TRPX_DEVICE void st_stream(u32* p, u32 v) { __stcs(p, v); }
+TRPX_DEVICE void st_stream(uint4* p, uint4 v) { __stcs(p, v); }
+
+TRPX_DEVICE u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier (shared::cta) ----
+TRPX_DEVICE void mbar_init(u64* bar, u32 count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+TRPX_DEVICE void mbar_init_fence()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+TRPX_DEVICE void mbar_arrive_expect_tx(u64* bar, u32 bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
+                 : "memory");
+}
+TRPX_DEVICE bool mbar_try_wait(u64* bar, u32 parity)
+{
+    u32 ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+TRPX_DEVICE void mbar_wait(u64* bar, u32 parity)
+{
+    // bounded: a mis-programmed barrier must trap, never hang the box
+    for (u32 spins = 0; !mbar_try_wait(bar, parity); ++spins)
+        if (spins > (1u << 26)) trap();
+}
+
+// ---- TMA bulk copies (1-D): SASS UBLKCP ----
+// global -> shared, completion counted in bytes on `bar`; src/dst 16-byte aligned, bytes % 16 == 0
+TRPX_DEVICE void bulk_g2s(void* smem_dst, const void* gsrc, u32 bytes, u64* bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_addr(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(smem_addr(bar))
+        : "memory");
+}
+// shared -> global (bulk async-group)
+TRPX_DEVICE void bulk_s2g(void* gdst, const void* smem_src, u32 bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                 "r"(smem_addr(smem_src)), "r"(bytes)
+                 : "memory");
+}
+TRPX_DEVICE void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until the bulk groups of this thread have finished READING shared memory
+TRPX_DEVICE void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+TRPX_DEVICE void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// make generic-proxy shared-memory writes visible to the async proxy (before bulk_s2g)
+TRPX_DEVICE void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch(void (*kern)(KArgs...), u32 grid, u32 block, size_t smem, cudaStream_t st,
+                          Args... args)
+{
+    kern<<<grid, block, smem, st>>>(KArgs(args)...);
+    return cudaGetLastError();
+}
+
+#else
+// ----------------------------------------------------------------------------- emulation backend
+#define TRPX_DEVICE inline
+#define TRPX_HD inline
+#define TRPX_KERNEL
+#define TRPX_SHARED static
+#define TRPX_DYN_SMEM(name) unsigned char* name = ::emu::dyn_smem()
+#define TRPX_LAUNCH_BOUNDS(t, b)
+
+using ::emu::uint4;
+using ::emu::make_uint4;
+
+inline u32 tid() { return ::emu::cur().tid; }
+inline u32 bid() { return ::emu::cur().bid; }
+inline u32 nthreads() { return ::emu::cur().block_dim; }
+inline u32 nblocks() { return ::emu::cur().grid_dim; }
+inline void sync_block() { ::emu::sync_block(); }
+inline void sync_warp() { ::emu::sync_warp(); }
+inline void spin_hint() { ::emu::yield(); }
+inline void trap() { ::emu::trap(); }
+
+inline u32 shfl(u32 v, int src) { return (u32)::emu::shfl(v, src & 31); }
+inline u64 shfl(u64 v, int src) { return ::emu::shfl(v, src & 31); }
+inline u32 shfl_up(u32 v, int d) { return (u32)::emu::shfl_up(v, d); }
+inline u64 shfl_up(u64 v, int d) { return ::emu::shfl_up(v, d); }
+inline u32 shfl_down(u32 v, int d) { return (u32)::emu::shfl_down(v, d); }
+inline u32 shfl_xor(u32 v, int m) { return (u32)::emu::shfl(v, (int)(::emu::cur().tid & 31) ^ m); }
+inline u32 ballot(bool p) { return ::emu::ballot(p); }
+inline bool all_lanes(bool p) { return ::emu::ballot(p) == ::emu::ballot(true); }
+inline bool any_lane(bool p) { return ::emu::ballot(p) != 0; }
+inline u32 warp_max(u32 v) { return ::emu::warp_reduce(v, 0); }
+inline u32 warp_or(u32 v) { return ::emu::warp_reduce(v, 1); }
+inline u32 warp_add(u32 v) { return ::emu::warp_reduce(v, 2); }
+
+inline int clz32(u32 x) { return x ? __builtin_clz(x) : 32; }
+inline int clz64(u64 x) { return x ? __builtin_clzll(x) : 64; }
+inline int ffs32(u32 x) { return __builtin_ffs((int)x); }
+inline int ffs64(u64 x) { return __builtin_ffsll((long long)x); }
+inline int popc32(u32 x) { return __builtin_popcount(x); }
+inline u32 funnel_r(u32 lo, u32 hi, u32 sh)
+{
+    sh &= 31;
+    return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+}
+inline u32 funnel_l(u32 lo, u32 hi, u32 sh)
+{
+    sh &= 31;
+    return sh ? (hi << sh) | (lo >> (32 - sh)) : hi;
+}
+inline u32 vabs2(u32 x)
+{
+    u32 r = 0;
+    for (int k = 0; k < 2; ++k) {
+        int16_t v = (int16_t)(x >> (16 * k));
+        uint16_t a = (uint16_t)(v < 0 ? (uint16_t)(0u - (uint16_t)v) : (uint16_t)v);
+        r |= (u32)a << (16 * k);
+    }
+    return r;
+}
+inline u32 vabs4(u32 x)
+{
+    u32 r = 0;
+    for (int k = 0; k < 4; ++k) {
+        int8_t v = (int8_t)(x >> (8 * k));
+        uint8_t a = (uint8_t)(v < 0 ? (uint8_t)(0u - (uint8_t)v) : (uint8_t)v);
+        r |= (u32)a << (8 * k);
+    }
+    return r;
+}
+
+inline u32 atomic_add(u32* p, u32 v) { u32 o = *p; *p = o + v; return o; }
+inline u64 atomic_add(u64* p, u64 v) { u64 o = *p; *p = o + v; return o; }
+inline u32 atomic_or(u32* p, u32 v) { u32 o = *p; *p = o | v; return o; }
+inline u32 atomic_max(u32* p, u32 v) { u32 o = *p; if (v > o) *p = v; return o; }
+
+inline u64 ld_relaxed(const u64* p) { return *(const volatile u64*)p; }
+inline void st_relaxed(u64* p, u64 v) { *(volatile u64*)p = v; }
+inline u32 ld_relaxed(const u32* p) { return *(const volatile u32*)p; }
+inline u32 ld_stream(const u32* p) { return *p; }
+inline void st_stream(u32* p, u32 v) { *p = v; }
+inline void st_stream(uint4* p, uint4 v) { *p = v; }
+
+inline void mbar_init(u64* bar, u32 count) { ::emu::mbar_init(bar, count); }
+inline void mbar_init_fence() {}
+inline void mbar_arrive_expect_tx(u64* bar, u32 bytes) { ::emu::mbar_arrive_expect_tx(bar, bytes); }
+inline void mbar_wait(u64* bar, u32 parity) { ::emu::mbar_wait(bar, parity); }
+inline void bulk_g2s(void* d, const void* s, u32 bytes, u64* bar) { ::emu::bulk_g2s(d, s, bytes, bar); }
+inline void bulk_s2g(void* d, const void* s, u32 bytes) { ::emu::bulk_s2g(d, s, bytes); }
+inline void bulk_commit() {}
+inline void bulk_wait_read0() {}
+inline void bulk_wait_all0() {}
+inline void fence_async_smem() {}
+
+using ::emu::cudaError_t;
+using ::emu::cudaStream_t;
+using ::emu::cudaSuccess;
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch(void (*kern)(KArgs...), u32 grid, u32 block, size_t smem, cudaStream_t,
+                          Args... args)
+{
+    ::emu::run_grid(grid, block, smem, [&]() { kern(KArgs(args)...); });
+    return cudaSuccess;
+}
+#endif
+
+// ----------------------------------------------------------------------------- shared helpers
+TRPX_HD u32 lane_of(u32 t) { return t & 31; }
+TRPX_HD u32 warp_of(u32 t) { return t >> 5; }
+TRPX_HD u64 div_up(u64 a, u64 b) { return (a + b - 1) / b; }
+
+}  // namespace trpx

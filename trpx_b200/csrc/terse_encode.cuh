@@ -1,0 +1,655 @@
+// terse_encode.cuh -- TERSE encoder for sm_100a: ONE fused pass over the pixels.
+//
+// Replaces Terse::f_compress (reference include/Terse.hpp:500-549) and what it calls:
+//   K1 block width     <- OR-reduce + f_highest_set_bit       Terse.hpp:508-515, :551-560
+//   K2 header/length   <- header emit                         Terse.hpp:517-535
+//   K3 offsets         <- the serial Bit_pointer walk         Terse.hpp:504, :519-540, size rule :547
+//   K4 bit packing     <- Bit_range::append_range             Bit_pointer.hpp:700-730
+//
+// Shape of the computation:
+//   * The stack is ONE bit stream; a frame end rounds the position up to "1 + floor(bits/8)" bytes
+//     (Terse.hpp:547).  A tile is a run of blocks inside one frame; its effect on the stream position
+//     is P -> P + bits, or align(P + bits) when it ends its frame.  Those maps compose into
+//     (has_end, a, c): P -> has_end ? align(P + a) + c : P + a, which is what the single-pass
+//     decoupled look-back carries from tile to tile -- no second pass over the pixels, no
+//     per-frame kernel.
+//   * A persistent CTA takes tiles by ticket, prefetches the next tile with a TMA bulk copy
+//     (cp.async.bulk + mbarrier) while it works on the current one, keeps each thread's 48 bytes
+//     (4 / 2 / 1 blocks of 12 u8 / u16 / u32 values) in registers, packs the tile's bits into a
+//     shared-memory staging area in tile-relative coordinates (so packing does not wait for the
+//     look-back), then shifts the staging words by the tile's global bit offset while storing them
+//     coalesced.  The word two tiles share is written by the later tile, which receives the earlier
+//     tile's bits through a 64-bit hand-off word -- no global atomics, no pre-zeroed output.
+#pragma once
+
+#include "simt.cuh"
+
+namespace trpx {
+
+// ------------------------------------------------------------------ look-back descriptors
+// One 64-bit word per tile: [63:62] status, [61] "tile ends its frame", [60:0] value.
+// AGG: value = bits of the tile; INCL: value = stream position (bits) after the tile.
+constexpr u64 ST_INVALID = 0, ST_AGG = 1, ST_INCL = 2;
+constexpr int ST_SHIFT = 62;
+constexpr u64 ENDS_BIT = 1ull << 61;
+constexpr u64 VAL_MASK = ENDS_BIT - 1;
+constexpr u64 TAIL_VALID = 1ull << 32;
+
+// frame end: the frame occupies 1 + floor(bits/8) bytes (Terse.hpp:547); the next frame starts there
+TRPX_HD u64 align_frame(u64 bits) { return ((bits >> 3) + 1) << 3; }
+
+struct FrameFn { u32 h; u64 a, c; };   // P -> h ? align_frame(P + a) + c : P + a
+TRPX_HD FrameFn fn_identity() { FrameFn f; f.h = 0; f.a = 0; f.c = 0; return f; }
+// g o f, where f is one tile (applied first): f(P) = ends ? align_frame(P + bits) : P + bits
+TRPX_HD FrameFn fn_after_tile(FrameFn g, bool ends, u64 bits)
+{
+    FrameFn r;
+    if (!ends) { r.h = g.h; r.a = g.a + bits; r.c = g.c; return r; }
+    r.h = 1;
+    r.a = bits;
+    // f(P) is a multiple of 8, so align_frame(f(P) + a) = f(P) + align_frame(a)
+    r.c = g.h ? align_frame(g.a) + g.c : g.a;
+    return r;
+}
+TRPX_HD u64 fn_apply(FrameFn g, u64 P) { return g.h ? align_frame(P + g.a) + g.c : P + g.a; }
+
+struct EncParams {
+    const void* pixels;     // n_frames x n_values, frame-major
+    u64 n_values;           // values per frame
+    u64 n_frames;
+    u32 block;              // values per block (12 on the fast path)
+    u64 nblocks;            // blocks per frame
+    u64 tiles_per_frame;
+    u64 n_tiles;
+    u32* out_words;         // payload, 4-byte aligned
+    u64 out_capacity;       // bytes
+    u64* frame_ends;        // [n_frames] end byte offset of each frame
+    u32* prolix_bits;       // [1], zeroed
+    u32* status;            // [1], zeroed
+    u64* desc;              // [n_tiles] zeroed
+    u64* tails;             // [n_tiles] zeroed
+    u32* ticket;            // [1] zeroed
+    u32 dbg_incl_stride;    // tests only: publish INCL for every k-th tile only (0 = always)
+};
+
+// ------------------------------------------------------------------ pixel-type traits
+template <typename T>
+struct Pix {
+    static constexpr int SZ = (int)sizeof(T);
+    static constexpr int W = 8 * SZ;
+    static constexpr bool SGN = T(-1) < T(0);
+    static constexpr int UNIT_BYTES = SZ == 8 ? 96 : 48;    // bytes one thread owns (3 or 6 LDS.128)
+    static constexpr int UW = UNIT_BYTES / 4;               // 32-bit words per unit
+    static constexpr int VPU = UNIT_BYTES / SZ;             // values per unit: 48 / 24 / 12 / 12
+    static constexpr int BPU = VPU / 12;                    // blocks per unit:  4 /  2 /  1 /  1
+    static constexpr int BW = 12 * SZ / 4;                  // words per block:  3 /  6 / 12 / 24
+    static constexpr int MAXBITS = 12 + 12 * (W + (SGN ? 1 : 0));   // worst block: header + data
+};
+
+TRPX_HD u32 abs32(u32 x) { u32 sx = (u32)((int)x >> 31); return (x ^ sx) - sx; }
+TRPX_HD u64 abs64(u64 x) { u64 sx = (u64)((i64)x >> 63); return (x ^ sx) - sx; }
+
+// K1: significant bits of a full 12-value block held in BW words (Terse.hpp:508-515, :551-560)
+template <typename T>
+TRPX_DEVICE u32 block_width12(const u32* w)
+{
+    typedef Pix<T> P;
+    u32 s;
+    bool nz;
+    if (P::SZ == 8) {
+        u64 m = 0;
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+            u64 v = (u64)w[2 * j] | ((u64)w[2 * j + 1] << 32);
+            m |= P::SGN ? abs64(v) : v;
+        }
+        s = 64 - (u32)clz64(m);
+        nz = m != 0;
+    } else {
+        u32 m = 0;
+#pragma unroll
+        for (int j = 0; j < P::BW; ++j)
+            m |= !P::SGN ? w[j] : P::SZ == 1 ? vabs4(w[j]) : P::SZ == 2 ? vabs2(w[j]) : abs32(w[j]);
+        if (P::SZ == 1) { m |= m >> 16; m |= m >> 8; m &= 0xffu; }
+        if (P::SZ == 2) { m |= m >> 16; m &= 0xffffu; }
+        s = 32 - (u32)clz32(m);
+        nz = m != 0;
+    }
+    if (P::SGN && nz) s += 1;
+    return s;
+}
+
+// K2: block header (Terse.hpp:517-535): value (LSB first) and length 1 / 4 / 6 / 12
+TRPX_HD void block_header(u32 s, u32 prev, u32& hv, u32& hl)
+{
+    if (s == prev) { hv = 1; hl = 1; }
+    else if (s < 7) { hv = s << 1; hl = 4; }
+    else if (s < 10) { hv = (0x7u | ((s - 7) << 3)) << 1; hl = 6; }
+    else { hv = (0x1Fu | ((s - 10) << 5)) << 1; hl = 12; }
+}
+
+// ------------------------------------------------------------------ K4: per-thread bit sink
+// Appends fields LSB-first (Bit_pointer.hpp:700-730) at a tile-relative bit offset.  Complete
+// 32-bit words go to shared memory with plain stores, except the thread's FIRST word (shared with
+// its predecessor) which stays in `head`, and the unfinished LAST word which stays in `acc`; both
+// are resolved by merge_and_flush().
+struct BitSink {
+    u32* stg;
+    u64 acc;
+    u32 w, nb, w0, head;
+    bool crossed;
+    TRPX_DEVICE void init(u32* stg_, u32 off)
+    {
+        stg = stg_; w0 = w = off >> 5; nb = off & 31; acc = 0; head = 0; crossed = false;
+    }
+    TRPX_DEVICE void put(u32 v, u32 n)     // n in [0, 32], v < 2^n
+    {
+        acc |= (u64)v << nb;
+        nb += n;
+        if (nb >= 32) {
+            u32 lo = (u32)acc;
+            if (!crossed) { head = lo; crossed = true; } else stg[w] = lo;
+            ++w;
+            acc >>= 32;
+            nb -= 32;
+        }
+    }
+    TRPX_DEVICE void put_wide(u64 v, u32 s)   // low s bits of the sign-extended value, s in [1, 65]
+    {
+        u32 n0 = s < 32 ? s : 32;
+        u32 lo = (u32)v;
+        if (n0 < 32) lo &= (1u << n0) - 1;
+        put(lo, n0);
+        if (s > 32) {
+            u32 n1 = s - 32 < 32 ? s - 32 : 32;
+            u32 hi = (u32)(v >> 32);
+            if (n1 < 32) hi &= (1u << n1) - 1;
+            put(hi, n1);
+        }
+        if (s > 64) put((u32)(v >> 63) & 1u, 1);
+    }
+};
+
+// value i of a block held in words, as a sign-extended 64-bit pattern
+template <typename T>
+TRPX_DEVICE u64 block_value(const u32* w, int i)
+{
+    typedef Pix<T> P;
+    if (P::SZ == 1) { u32 b = (w[i >> 2] >> (8 * (i & 3))) & 0xffu; return P::SGN ? (u64)(i64)(int8_t)b : b; }
+    if (P::SZ == 2) { u32 h = (w[i >> 1] >> (16 * (i & 1))) & 0xffffu; return P::SGN ? (u64)(i64)(int16_t)h : h; }
+    if (P::SZ == 4) return P::SGN ? (u64)(i64)(int)w[i] : (u64)w[i];
+    return (u64)w[2 * i] | ((u64)w[2 * i + 1] << 32);
+}
+
+// K4: the data of one block (cnt values of s bits).  Full blocks of the common widths are merged
+// pairwise / quadwise in registers first (all fields of a block share s), so a 12-value block costs
+// 3 (s <= 8) or 6 sink operations instead of 12.
+template <typename T>
+TRPX_DEVICE void pack_block12(BitSink& sk, const u32* w, u32 s, u32 cnt)
+{
+    typedef Pix<T> P;
+    if (s == 0) return;
+    if (cnt == 12) {
+        if (P::SZ == 2 && s <= 16) {
+            const u32 m = P::SGN ? ((1u << s) - 1) * 0x00010001u : 0xffffffffu;   // s<=16: per-half mask
+            if (s <= 8) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    u32 x0 = w[2 * q] & m, x1 = w[2 * q + 1] & m;
+                    u32 p0 = (x0 & 0xffffu) | ((x0 >> 16) << s);
+                    u32 p1 = (x1 & 0xffffu) | ((x1 >> 16) << s);
+                    sk.put(p0 | (p1 << (2 * s)), 4 * s);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    u32 x = w[q] & m;
+                    if (s == 16) sk.put(x, 32);
+                    else sk.put((x & 0xffffu) | ((x >> 16) << s), 2 * s);
+                }
+            }
+            return;
+        }
+        if (P::SZ == 1 && s <= 8) {
+            const u32 m = P::SGN ? ((1u << s) - 1) * 0x00010001u : 0x00ff00ffu;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                u32 a = w[q] & 0x00ff00ffu & m, b = (w[q] >> 8) & 0x00ff00ffu & m;
+                u32 pr = a | (b << s);                               // two 16-bit lanes of 2s bits
+                if (s == 8) sk.put(pr, 32);
+                else sk.put((pr & 0xffffu) | ((pr >> 16) << (2 * s)), 4 * s);
+            }
+            return;
+        }
+        if (P::SZ == 4 && s <= 32) {
+            const u32 m = s == 32 ? 0xffffffffu : (1u << s) - 1;
+#pragma unroll
+            for (int i = 0; i < 12; ++i) sk.put(w[i] & m, s);
+            return;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i)
+        if ((u32)i < cnt) sk.put_wide(block_value<T>(w, i), s);
+}
+
+// ------------------------------------------------------------------ K3: block-wide exclusive scan
+// len -> tile-relative bit offset; warp shuffles + one shared round.  Contains ONE sync_block().
+template <int NT>
+TRPX_DEVICE void scan_lengths(u32 len, u32* sm_warp_tot, u32& off, u32& tile_bits)
+{
+    const u32 t = tid(), lane = t & 31, warp = t >> 5;
+    u32 incl = len;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u32 v = shfl_up(incl, d);
+        if (lane >= (u32)d) incl += v;
+    }
+    if (lane == 31) sm_warp_tot[warp] = incl;
+    sync_block();
+    u32 base = 0, total = 0;
+#pragma unroll
+    for (int i = 0; i < NT / 32; ++i) {
+        u32 v = sm_warp_tot[i];
+        if ((u32)i < warp) base += v;
+        total += v;
+    }
+    off = base + incl - len;
+    tile_bits = total;
+}
+
+// Words that several warps may touch (each warp's first word, and the word after the tile's last bit)
+// are accumulated with shared-memory atomics and therefore zeroed first.  Caller syncs afterwards.
+template <int NT>
+TRPX_DEVICE void zero_boundary_words(u32* stg, u32 off, u32 tile_bits)
+{
+    const u32 t = tid();
+    if ((t & 31) == 0) stg[off >> 5] = 0;
+    if (t == NT - 1) stg[tile_bits >> 5] = 0;
+}
+
+// Resolve the partial words inside a warp without atomics.  OR of disjoint bit fields == ADD, so
+// the bits carried into lane t's first word are a difference of two warp prefix sums of the lanes'
+// unfinished last words: sum over lanes [p, t) where p is the last lane before t that completed a
+// word.  Only the warp's first completed word and its outgoing tail can be shared with other warps;
+// those two use shared-memory atomics (<= 2 per warp per tile).
+TRPX_DEVICE void merge_and_flush(BitSink& sk, u32 end_off)
+{
+    const u32 lane = tid() & 31;
+    const u32 tail = (u32)sk.acc;
+    u32 incl = tail;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u32 v = shfl_up(incl, d);
+        if (lane >= (u32)d) incl += v;
+    }
+    const u32 excl = incl - tail;
+    const u32 cmask = ballot(sk.crossed);
+    const u32 below = cmask & ((1u << lane) - 1);
+    const u32 qp = shfl(excl, below ? 31 - clz32(below) : 0);
+    const u32 carry = excl - (below ? qp : 0u);
+    if (sk.crossed) {
+        u32 word = sk.head | carry;
+        if (below == 0) atomic_or(&sk.stg[sk.w0], word);
+        else sk.stg[sk.w0] = word;
+    }
+    const u32 ql = shfl(excl, cmask ? 31 - clz32(cmask) : 0);
+    if (lane == 31) {
+        u32 out = incl - (cmask ? ql : 0u);
+        if (out) atomic_or(&sk.stg[end_off >> 5], out);
+    }
+}
+
+// Decoupled look-back over the frame-aware position maps; executed by one whole warp.
+// Returns the stream position (bits) at which `tile` starts.
+TRPX_DEVICE u64 lookback_start(const u64* desc, u64 tile)
+{
+    if (tile == 0) return 0;
+    const u32 lane = tid() & 31;
+    FrameFn g = fn_identity();
+    i64 base = (i64)tile - 1;
+    for (;;) {
+        const i64 idx = base - (i64)lane;
+        u64 d;
+        u32 first_incl;
+        for (u32 spins = 0;; ++spins) {
+            d = idx >= 0 ? ld_relaxed(&desc[idx]) : (ST_INCL << ST_SHIFT);   // "tile -1": position 0
+            const u32 st = (u32)(d >> ST_SHIFT);
+            const u32 incl_mask = ballot(st == ST_INCL);
+            const u32 inval_mask = ballot(st == ST_INVALID);
+            first_incl = incl_mask ? (u32)ffs32(incl_mask) - 1 : 32;
+            const u32 needed = first_incl >= 32 ? 0xffffffffu : ((1u << first_incl) - 1);
+            if ((inval_mask & needed) == 0) break;
+            if (spins > (1u << 24)) trap();               // never hang the device
+            spin_hint();
+        }
+        for (u32 l = 0; l < first_incl; ++l) {            // nearest tile first: g <- g o f_l
+            const u64 dl = shfl(d, (int)l);
+            g = fn_after_tile(g, (dl & ENDS_BIT) != 0, dl & VAL_MASK);
+        }
+        if (first_incl < 32) return fn_apply(g, shfl(d, (int)first_incl) & VAL_MASK);
+        base -= 32;
+    }
+}
+
+// Shared by both encoder kernels: after the tile's bits sit in `stg` (tile-relative), find the
+// tile's stream position, publish it, and store the words this tile owns, shifted into place.
+//   bc[0] = P0, bc[1] = tail_in        (written by thread 0, read by all after the sync)
+template <int NT>
+TRPX_DEVICE void resolve_and_store(const EncParams& p, u64 tile, bool ends, u32 tile_bits,
+                                   const u32* stg, u64* bc)
+{
+    const u32 t = tid();
+    const u32 nstg = (tile_bits + 31) >> 5;
+    // word i of this tile's output window (without the predecessor's bits of word 0)
+    auto word_at = [&](u32 i, u32 sh) -> u32 {
+        u32 lo = (i >= 1 && i - 1 < nstg) ? stg[i - 1] : 0u;
+        u32 hi = i < nstg ? stg[i] : 0u;
+        return funnel_l(lo, hi, sh);
+    };
+    if (t < 32) {
+        const u64 P0 = lookback_start(p.desc, tile);
+        if (t == 0) {
+            const u64 Pn = ends ? align_frame(P0 + tile_bits) : P0 + tile_bits;
+            if (p.dbg_incl_stride == 0 || tile % p.dbg_incl_stride == 0)
+                st_relaxed(&p.desc[tile], (ST_INCL << ST_SHIFT) | Pn);
+            const u32 k = (u32)((Pn >> 5) - (P0 >> 5));
+            const u32 sh = (u32)(P0 & 31);
+            // Our bits of the word the NEXT tile starts in.  When we own a complete word (k >= 1)
+            // they do not depend on our predecessor: publish before waiting, so the hand-off never
+            // forms a chain across tiles.
+            u32 tout = word_at(k, sh);
+            if (k >= 1) st_relaxed(&p.tails[tile], TAIL_VALID | (u64)tout);
+            u64 tin = 0;
+            if (sh != 0) {                                 // the word we start in is ours to store:
+                for (u32 spins = 0;; ++spins) {            // fetch the predecessor's bits of it
+                    tin = ld_relaxed(&p.tails[tile - 1]);
+                    if (tin & TAIL_VALID) break;
+                    if (spins > (1u << 24)) trap();
+                    spin_hint();
+                }
+            }
+            tin &= 0xffffffffull;
+            if (k == 0) { tout |= (u32)tin; st_relaxed(&p.tails[tile], TAIL_VALID | (u64)tout); }
+            bc[0] = P0;
+            bc[1] = tin;
+            bc[2] = tout;
+        }
+    }
+    sync_block();
+    const u64 P0 = bc[0];
+    const u32 tail_in = (u32)bc[1];
+    const u64 Pn = ends ? align_frame(P0 + tile_bits) : P0 + tile_bits;
+    const u64 W0 = P0 >> 5, Wn = Pn >> 5;
+    const u32 sh = (u32)(P0 & 31);
+    const u32 k = (u32)(Wn - W0);                          // complete words this tile owns
+    const bool fits = ((Pn + 7) >> 3) <= p.out_capacity;
+    if (fits) {
+        for (u32 i = t; i < k; i += NT) st_stream(&p.out_words[W0 + i], word_at(i, sh) | (i == 0 ? tail_in : 0u));
+    } else if (t == 0) {
+        atomic_max(p.status, 2u);                          // TRPX_ERR_CAPACITY
+    }
+    if (t == 0) {
+        if (ends) p.frame_ends[tile / p.tiles_per_frame] = Pn >> 3;
+        if (tile + 1 == p.n_tiles && fits) {               // nobody follows: store the final bytes
+            const u32 tout = (u32)bc[2];
+            unsigned char* ob = (unsigned char*)p.out_words;
+            for (u32 b = 0; b < (u32)((Pn >> 3) & 3); ++b) ob[Wn * 4 + b] = (unsigned char)(tout >> (8 * b));
+        }
+    }
+}
+
+// ------------------------------------------------------------------ shared-memory layout
+constexpr int ENC_STAGES = 2;
+constexpr int SM_BARS = 0;          // ENC_STAGES mbarriers, 16 bytes apart
+constexpr int SM_TICKETS = 64;      // ENC_STAGES u32
+constexpr int SM_WARP_TOT = 128;    // 32 u32
+constexpr int SM_WARP_LAST = 256;   // 32 u32
+constexpr int SM_BCAST = 384;       // 4 u64
+constexpr int SM_MAX = 448;         // u32 running max width
+constexpr int SM_HEADER = 512;
+
+template <typename T, int NT>
+struct EncGeom {
+    typedef Pix<T> P;
+    static constexpr int TILE_BYTES = NT * P::UNIT_BYTES;
+    static constexpr int TILE_BLOCKS = NT * P::BPU;
+    static constexpr int STAGE_BYTES = ((P::UNIT_BYTES + TILE_BYTES + 127) / 128) * 128;   // halo + tile
+    static constexpr int STG_WORDS = (TILE_BLOCKS * P::MAXBITS + 31) / 32 + 4;
+    static constexpr int SMEM_BYTES = SM_HEADER + ENC_STAGES * STAGE_BYTES + STG_WORDS * 4;
+};
+
+// ------------------------------------------------------------------ fast kernel: block == 12, 16-byte aligned frames
+template <typename T, int NT>
+TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) terse_encode_kernel(EncParams p)
+{
+    typedef Pix<T> P;
+    typedef EncGeom<T, NT> G;
+    TRPX_DYN_SMEM(sm);
+    u64* bars = (u64*)(sm + SM_BARS);
+    u32* tickets = (u32*)(sm + SM_TICKETS);
+    u32* sm_warp_tot = (u32*)(sm + SM_WARP_TOT);
+    u32* sm_warp_last = (u32*)(sm + SM_WARP_LAST);
+    u64* bc = (u64*)(sm + SM_BCAST);
+    u32* sm_max = (u32*)(sm + SM_MAX);
+    unsigned char* stages = sm + SM_HEADER;
+    u32* stg = (u32*)(stages + ENC_STAGES * G::STAGE_BYTES);
+
+    const u32 t = tid(), lane = t & 31, warp = t >> 5;
+    const u64 frame_bytes = p.n_values * P::SZ;
+
+    // thread 0 is the TMA producer: take the next ticket, start that tile's bulk copy
+    auto issue = [&](int s) {
+        const u32 tk = atomic_add(p.ticket, 1u);
+        tickets[s] = tk;
+        if ((u64)tk < p.n_tiles) {
+            const u64 f = tk / p.tiles_per_frame, tif = tk % p.tiles_per_frame;
+            const u64 tile_off = tif * (u64)G::TILE_BYTES;
+            u64 bytes = frame_bytes - tile_off;
+            if (bytes > (u64)G::TILE_BYTES) bytes = G::TILE_BYTES;
+            const unsigned char* src = (const unsigned char*)p.pixels + f * frame_bytes + tile_off;
+            unsigned char* dst = stages + s * G::STAGE_BYTES + P::UNIT_BYTES;
+            if (tif > 0) { src -= P::UNIT_BYTES; dst -= P::UNIT_BYTES; bytes += P::UNIT_BYTES; }   // halo: previous block
+            mbar_arrive_expect_tx(&bars[2 * s], (u32)bytes);
+            bulk_g2s(dst, src, (u32)bytes, &bars[2 * s]);
+        }
+    };
+
+    if (t == 0) {
+        for (int s = 0; s < ENC_STAGES; ++s) mbar_init(&bars[2 * s], 1);
+        mbar_init_fence();
+        *sm_max = 0;
+    }
+    sync_block();
+    if (t == 0)
+        for (int s = 0; s < ENC_STAGES; ++s) issue(s);
+    sync_block();
+
+    u32 my_max = 0;
+    for (u32 it = 0;; ++it) {
+        const int s = (int)(it % ENC_STAGES);
+        const u64 tile = tickets[s];
+        if (tile >= p.n_tiles) break;
+        const u64 tif = tile % p.tiles_per_frame;
+        const bool ends = tif + 1 == p.tiles_per_frame;
+        const u64 first_val = tif * (u64)(G::TILE_BLOCKS * 12);
+        u64 tile_vals = p.n_values - first_val;
+        if (tile_vals > (u64)(G::TILE_BLOCKS * 12)) tile_vals = G::TILE_BLOCKS * 12;
+
+        mbar_wait(&bars[2 * s], (it / ENC_STAGES) & 1);
+
+        // ---- this thread's unit -> registers
+        u32 w[P::UW];
+        const unsigned char* tile_sm = stages + s * G::STAGE_BYTES + P::UNIT_BYTES;
+        {
+            const uint4* src = (const uint4*)(tile_sm + (size_t)t * P::UNIT_BYTES);
+#pragma unroll
+            for (int j = 0; j < P::UW / 4; ++j) {
+                uint4 v = src[j];
+                w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
+            }
+        }
+        const u64 my_first = (u64)t * P::VPU;
+        u32 nvalid = my_first >= tile_vals ? 0u : (tile_vals - my_first > (u64)P::VPU ? (u32)P::VPU : (u32)(tile_vals - my_first));
+        if (nvalid < (u32)P::VPU) {                        // frame tail: wipe what is not ours
+            const u32 vbytes = nvalid * P::SZ;
+#pragma unroll
+            for (int j = 0; j < P::UW; ++j) {
+                const u32 lo = 4u * j;
+                if (vbytes <= lo) w[j] = 0;
+                else if (vbytes < lo + 4) w[j] &= (1u << (8 * (vbytes - lo))) - 1;
+            }
+        }
+
+        // ---- K1: widths of my blocks
+        u32 sb[P::BPU], cnt[P::BPU];
+#pragma unroll
+        for (int b = 0; b < P::BPU; ++b) {
+            sb[b] = block_width12<T>(&w[b * P::BW]);
+            const u32 v0 = 12u * b;
+            cnt[b] = nvalid <= v0 ? 0u : (nvalid - v0 > 12u ? 12u : nvalid - v0);
+            my_max = sb[b] > my_max ? sb[b] : my_max;
+        }
+        u32 prev0 = 0;                                     // width of the block before the tile
+        if (t == 0 && tif > 0) {
+            u32 h[P::BW];
+            const u32* hs = (const u32*)(tile_sm - 4 * P::BW);
+#pragma unroll
+            for (int j = 0; j < P::BW; ++j) h[j] = hs[j];
+            prev0 = block_width12<T>(h);
+        }
+        if (lane == 31) sm_warp_last[warp] = sb[P::BPU - 1];
+        sync_block();                                      // A: stage `s` is free, warp_last visible
+        if (t == 0) issue(s);
+
+        // ---- K2: headers and lengths
+        u32 prev = shfl_up(sb[P::BPU - 1], 1);
+        if (lane == 0) prev = warp > 0 ? sm_warp_last[warp - 1] : prev0;
+        u32 hv[P::BPU], hl[P::BPU], len = 0;
+#pragma unroll
+        for (int b = 0; b < P::BPU; ++b) {
+            hv[b] = 0; hl[b] = 0;
+            if (cnt[b]) {
+                block_header(sb[b], prev, hv[b], hl[b]);
+                len += hl[b] + sb[b] * cnt[b];
+                prev = sb[b];
+            }
+        }
+
+        // ---- K3: offsets inside the tile; publish the tile's bit count for the look-back
+        u32 off, tile_bits;
+        scan_lengths<NT>(len, sm_warp_tot, off, tile_bits);    // sync B inside
+        if (t == 0)
+            st_relaxed(&p.desc[tile], (ST_AGG << ST_SHIFT) | (ends ? ENDS_BIT : 0) | (u64)tile_bits);
+        zero_boundary_words<NT>(stg, off, tile_bits);
+        sync_block();                                      // C
+
+        // ---- K4: pack into tile-relative staging
+        BitSink sk;
+        sk.init(stg, off);
+#pragma unroll
+        for (int b = 0; b < P::BPU; ++b)
+            if (cnt[b]) {
+                sk.put(hv[b], hl[b]);
+                pack_block12<T>(sk, &w[b * P::BW], sb[b], cnt[b]);
+            }
+        merge_and_flush(sk, off + len);
+        sync_block();                                      // D: staging complete
+
+        resolve_and_store<NT>(p, tile, ends, tile_bits, stg, bc);
+        // no barrier needed here: every shared word reused by the next iteration is rewritten only
+        // after one of its barriers A..D, which no thread passes before all finished this store.
+    }
+    my_max = warp_max(my_max);
+    if (lane == 0 && my_max) atomic_max(sm_max, my_max);
+    sync_block();
+    if (t == 0 && *sm_max) atomic_max(p.prolix_bits, *sm_max);
+}
+
+// ------------------------------------------------------------------ generic kernel: any block size / alignment
+// One thread per block, values read straight from global memory (two passes over the block's
+// values, the second one hits L1/L2).  Same scan, look-back, staging and store as the fast kernel.
+template <typename T, int NT>
+struct GenGeom {
+    static constexpr int STG_WORDS_MAX = (227 * 1024 - SM_HEADER) / 4 - 8;
+};
+
+template <typename T>
+TRPX_DEVICE u64 load_value(const T* px, u64 i)
+{
+    return Pix<T>::SGN ? (u64)(i64)px[i] : (u64)px[i];
+}
+
+template <typename T, int NT>
+TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) terse_encode_generic_kernel(EncParams p, u32 tile_blocks)
+{
+    typedef Pix<T> P;
+    TRPX_DYN_SMEM(sm);
+    u32* tickets = (u32*)(sm + SM_TICKETS);
+    u32* sm_warp_tot = (u32*)(sm + SM_WARP_TOT);
+    u32* sm_warp_last = (u32*)(sm + SM_WARP_LAST);
+    u64* bc = (u64*)(sm + SM_BCAST);
+    u32* sm_max = (u32*)(sm + SM_MAX);
+    u32* stg = (u32*)(sm + SM_HEADER);
+    const u32 t = tid(), lane = t & 31, warp = t >> 5;
+    const u64 tmask = P::W == 64 ? ~0ull : ((1ull << P::W) - 1);
+    if (t == 0) *sm_max = 0;
+    u32 my_max = 0;
+    for (;;) {
+        sync_block();                                      // previous tile fully stored; tickets reusable
+        if (t == 0) tickets[0] = atomic_add(p.ticket, 1u);
+        sync_block();
+        const u64 tile = tickets[0];
+        if (tile >= p.n_tiles) break;
+        const u64 f = tile / p.tiles_per_frame, tif = tile % p.tiles_per_frame;
+        const bool ends = tif + 1 == p.tiles_per_frame;
+        const T* px = (const T*)p.pixels + f * p.n_values;
+        const u64 blk = tif * tile_blocks + t;             // my block inside the frame
+        const bool have = t < tile_blocks && blk < p.nblocks;
+        const u64 from = blk * p.block;
+        u32 cnt = 0;
+        if (have) cnt = (u32)(p.n_values - from < (u64)p.block ? p.n_values - from : (u64)p.block);
+
+        auto width_of = [&](u64 v0, u32 n) -> u32 {         // Terse.hpp:508-515, :551-560
+            u64 m = 0;
+            for (u32 i = 0; i < n; ++i) {
+                u64 v = load_value<T>(px, v0 + i);
+                m |= (P::SGN ? abs64(v) : v) & tmask;
+            }
+            u32 s = 64 - (u32)clz64(m);
+            return (P::SGN && m) ? s + 1 : s;
+        };
+        u32 s = have ? width_of(from, cnt) : 0;
+        my_max = s > my_max ? s : my_max;
+        u32 prev0 = 0;
+        if (t == 0 && tif > 0) prev0 = width_of(from - p.block, p.block);
+        if (lane == 31) sm_warp_last[warp] = s;
+        sync_block();
+        u32 prev = shfl_up(s, 1);
+        if (lane == 0) prev = warp > 0 ? sm_warp_last[warp - 1] : prev0;
+        u32 hv = 0, hl = 0, len = 0;
+        if (have) { block_header(s, prev, hv, hl); len = hl + s * cnt; }
+        u32 off, tile_bits;
+        scan_lengths<NT>(len, sm_warp_tot, off, tile_bits);
+        if (t == 0)
+            st_relaxed(&p.desc[tile], (ST_AGG << ST_SHIFT) | (ends ? ENDS_BIT : 0) | (u64)tile_bits);
+        zero_boundary_words<NT>(stg, off, tile_bits);
+        sync_block();
+        BitSink sk;
+        sk.init(stg, off);
+        if (have) {
+            sk.put(hv, hl);
+            if (s)
+                for (u32 i = 0; i < cnt; ++i) sk.put_wide(load_value<T>(px, from + i), s);
+        }
+        merge_and_flush(sk, off + len);
+        sync_block();
+        resolve_and_store<NT>(p, tile, ends, tile_bits, stg, bc);
+    }
+    my_max = warp_max(my_max);
+    if (lane == 0 && my_max) atomic_max(sm_max, my_max);
+    sync_block();
+    if (t == 0 && *sm_max) atomic_max(p.prolix_bits, *sm_max);
+}
+
+}  // namespace trpx
