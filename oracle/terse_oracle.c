@@ -18,6 +18,8 @@
 #include <stdio.h>
 #include <string.h>
 
+static int dtype_signed(int dtype) { return dtype >= ORC_I8; }
+
 size_t orc_dtype_size(int dtype)
 {
     switch (dtype) {
@@ -29,11 +31,9 @@ size_t orc_dtype_size(int dtype)
     }
 }
 
-static int dtype_signed(int dtype) { return dtype >= ORC_I8; }
-
 size_t orc_max_frame_bytes(size_t n, int dtype, unsigned block)
 {
-    size_t w = 8 * orc_dtype_size(dtype) + 1;          /* signed T_MIN needs W+1 bits */
+    size_t w = 8 * orc_dtype_size(dtype) + (dtype_signed(dtype) ? 1 : 0);   /* signed T_MIN needs W+1 bits */
     size_t nblocks = (n + block - 1) / block;
     size_t bits = 12 * nblocks + n * w;
     return (bits + 7) / 8 + 1;

@@ -1,0 +1,115 @@
+"""Kernel-logic tests WITHOUT a GPU: trpx_b200/csrc/prolix_decode.cuh compiled for the host with the
+test-only SIMT emulator.  Streams come from the oracle (== reference bytes); tiny segments and short
+warm-ups force the speculative walkers to disagree so the verify / re-walk loop is exercised."""
+import numpy as np
+import pytest
+
+import emu_lib
+import golden_util as G
+import orc
+
+
+def roundtrip(stack, block=12, out_dtype=None, known_ends=True, **kw):
+    stack = np.ascontiguousarray(stack)
+    F, N = stack.shape
+    p, per, pb = orc.encode_stack(stack, block)
+    ends = np.cumsum(per).astype(np.uint64)
+    od = stack.dtype if out_dtype is None else np.dtype(out_dtype)
+    got, st, staged, fe = emu_lib.decode(p, N, F, stack.dtype.kind == "i", od, block,
+                                         ends if known_ends else None, **kw)
+    assert st == 0
+    if not known_ends:
+        assert np.array_equal(fe, ends)
+    want = np.stack([orc.decode_frame(p[int(ends[f] - per[f]):int(ends[f])], N, stack.dtype.kind == "i", od, block)[0]
+                     for f in range(F)])
+    assert np.array_equal(got, want)
+    if od == stack.dtype:
+        assert np.array_equal(got, stack)
+    return staged
+
+
+@pytest.mark.parametrize("c", G.load("kat_small"), ids=lambda c: c["name"])
+def test_small_kats(c):
+    a = G.small_input(c)
+    roundtrip(a[None, :], c["block"])
+
+
+@pytest.mark.parametrize("dt", list(range(8)), ids=lambda d: str(np.dtype(orc.NP_OF[d])))
+@pytest.mark.parametrize("seg,warm", [(64, 32), (256, 512), (4096, 4096)])
+def test_all_types_staged(dt, seg, warm):
+    isz = orc.NP_OF[dt]().itemsize
+    n = 12 * 1400 + 8
+    while (n * isz) % 16:
+        n += 1
+    st = np.stack([orc.kat_fill(dt, n, 90 + f) for f in range(3)])
+    assert roundtrip(st, seg_bytes=seg, warm_bytes=warm) is True
+
+
+def test_synthetic_frames_tiny_segments():
+    st = np.stack([orc.synth_frame(orc.U16, 128, 96, 2.0, 12, 1000 + f) for f in range(3)])
+    for seg, warm in [(16, 0), (48, 16), (512, 128), (100000, 64)]:
+        assert roundtrip(st, seg_bytes=seg, warm_bytes=warm) is True
+
+
+def test_sparse_and_zero_frames():
+    z = np.zeros((3, 12 * 4096), np.uint8)
+    roundtrip(z, seg_bytes=32, warm_bytes=16)            # zero-run skipping across segments and tiles
+    z[1, 5000] = 1
+    z[2, ::977] = 3
+    roundtrip(z, seg_bytes=32, warm_bytes=16)
+    roundtrip(z.astype(np.uint16), seg_bytes=64, warm_bytes=64)
+    roundtrip(z.astype(np.uint32), seg_bytes=4096, warm_bytes=64)
+
+
+def test_tiny_frames_many():
+    roundtrip(np.stack([orc.kat_fill(orc.U16, 8, 7 + f) for f in range(40)]))
+    roundtrip(np.zeros((50, 8), np.uint16))
+    roundtrip(np.stack([orc.kat_fill(orc.I16, 24, 7 + f) for f in range(9)]), seg_bytes=16, warm_bytes=8)
+
+
+def test_unknown_frame_sizes_are_recovered():
+    st = np.stack([orc.kat_fill(orc.U16, 1000, 7 + f) for f in range(5)])
+    roundtrip(st, known_ends=False)
+    roundtrip(st[:1], known_ends=False)
+
+
+@pytest.mark.parametrize("src,dst", [(np.uint16, np.uint8), (np.uint16, np.uint64), (np.uint16, np.int32),
+                                     (np.int16, np.int8), (np.int16, np.int64), (np.uint32, np.uint16),
+                                     (np.int32, np.int16), (np.uint8, np.uint32), (np.int64, np.int32)])
+def test_output_conversion_clamps_like_get_range(src, dst):
+    rng = np.random.default_rng(3)
+    info = np.iinfo(src)
+    a = rng.integers(max(info.min, -70000), min(info.max, 70000), size=(2, 12 * 300), endpoint=True).astype(src)
+    a[:, ::50] = info.max
+    if info.min < 0:
+        a[:, 7::50] = info.min + 1
+    roundtrip(a, out_dtype=dst)
+
+
+def test_signed_extremes_roundtrip():
+    a = np.array([-32768, 32767, -1, 0, 5, -5, 100, -100, 1, 2, 3, 4] * 4, np.int16)
+    roundtrip(a[None, :])
+    d = np.array([-2**63, 2**63 - 1, 0, -1] * 6, np.int64)
+    roundtrip(d[None, :])
+    e = np.array([2**64 - 1, 0, 1, 2**63] * 6, np.uint64)
+    roundtrip(e[None, :])
+
+
+@pytest.mark.parametrize("dt", [orc.U8, orc.U16, orc.I16, orc.U32, orc.I64])
+def test_generic_blocks_and_alignment(dt):
+    rng = np.random.default_rng(5 + dt)
+    for block, n, frames, mis in [(12, 1001, 3, 0), (7, 500, 2, 0), (1, 77, 2, 0), (40, 999, 3, 0),
+                                  (12, 1024, 2, 8), (5, 3, 4, 0), (300, 5000, 2, 0)]:
+        st = np.stack([orc.kat_fill(dt, n, int(rng.integers(1, 1 << 30))) for _ in range(frames)])
+        staged = roundtrip(st, block, seg_bytes=int(rng.integers(16, 300)), warm_bytes=int(rng.integers(0, 100)),
+                           misalign_out=mis)
+        if mis or block != 12 or (n * st.dtype.itemsize) % 16:
+            assert staged is False
+
+
+def test_truncated_payload_is_flagged():
+    st = np.stack([orc.kat_fill(orc.U16, 12 * 500, 3)])
+    p, per, pb = orc.encode_stack(st)
+    cut = p[: p.size // 2]
+    got, status, _, _ = emu_lib.decode(cut, st.shape[1], 1, False, np.uint16, 12, np.array([cut.size], np.uint64))
+    assert status == 4

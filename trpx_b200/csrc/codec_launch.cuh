@@ -95,6 +95,25 @@ inline void encode_launch_t(Launcher& L, const EncPlan& pl, EncParams p, u32 cta
     L.count();
 }
 
+template <typename T>
+inline const void* enc_kernel_t(bool fast)
+{
+    return fast ? (const void*)terse_encode_kernel<T, ENC_NT> : (const void*)terse_encode_generic_kernel<T, GEN_NT>;
+}
+inline const void* enc_kernel(int dtype, bool fast)
+{
+    switch (dtype) {
+    case DT_U8: return enc_kernel_t<uint8_t>(fast);
+    case DT_U16: return enc_kernel_t<uint16_t>(fast);
+    case DT_U32: return enc_kernel_t<uint32_t>(fast);
+    case DT_U64: return enc_kernel_t<uint64_t>(fast);
+    case DT_I8: return enc_kernel_t<int8_t>(fast);
+    case DT_I16: return enc_kernel_t<int16_t>(fast);
+    case DT_I32: return enc_kernel_t<int32_t>(fast);
+    default: return enc_kernel_t<int64_t>(fast);
+    }
+}
+
 // scratch: pl.scratch_bytes of device memory (any content).  d_prolix_bits / d_status: 1 x u32 each.
 inline void encode_async(Launcher& L, int dtype, const void* d_pixels, u64 n_values, u64 n_frames, u32 block,
                          void* d_out, u64 out_capacity, u64* d_frame_ends, u32* d_prolix_bits, u32* d_status,
@@ -131,6 +150,146 @@ inline void encode_async(Launcher& L, int dtype, const void* d_pixels, u64 n_val
     case DT_I32: encode_launch_t<int32_t>(L, pl, p, ctas_per_sm); break;
     default: encode_launch_t<int64_t>(L, pl, p, ctas_per_sm); break;
     }
+}
+
+// ---------------------------------------------------------------------------------- decode
+constexpr int WALK_NT = 64;       // threads per CTA of the P1 walkers (one stream segment per thread)
+constexpr int RESOLVE_NT = 256;   // threads per CTA of the cooperative verify / scan kernel
+constexpr int SEGTAB_NT = 1024;
+
+struct DecPlan {
+    bool staged;                  // block == 12 and 16-byte aligned frames: TMA-store unpack kernel
+    u64 nblocks, tiles_per_frame, n_tiles, max_segs;
+    u32 last_cnt, seg_bytes, warm_bytes;
+    size_t smem_unpack;
+    // scratch layout (byte offsets)
+    size_t off_frame_ends, off_seg_base, off_seg_frame, off_seg_entry, off_seg_exit, off_seg_count,
+        off_seg_b0, off_changed, off_zero_begin, off_widths, off_anchors, scratch_bytes;
+    bool ok;
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+inline DecPlan dec_plan(int out_dtype, u64 payload_bytes, u64 n_values, u64 n_frames, u32 block,
+                        const void* d_out, u32 seg_bytes, u32 warm_bytes)
+{
+    DecPlan pl;
+    const size_t so = dtype_size(out_dtype);
+    pl.ok = so != 0 && block != 0 && n_values != 0 && n_frames != 0;
+    pl.nblocks = div_up(n_values, block ? block : 1);
+    pl.last_cnt = (u32)(n_values - (pl.nblocks - 1) * block);
+    pl.tiles_per_frame = div_up(pl.nblocks, DEC_TB);
+    pl.n_tiles = pl.tiles_per_frame * n_frames;
+    if (pl.n_tiles >= (1ull << 31)) pl.ok = false;
+    pl.staged = block == 12 && ((uintptr_t)d_out & 15) == 0 && ((n_values * so) & 15) == 0;
+    pl.seg_bytes = seg_bytes < 16 ? 16 : seg_bytes;
+    pl.warm_bytes = warm_bytes;
+    pl.max_segs = payload_bytes / pl.seg_bytes + n_frames + 1;
+    pl.smem_unpack = 128 + DEC_TB + 16 + (size_t)DEC_TB * 4 + (pl.staged ? (size_t)DEC_TB * 12 * so : 0);
+    size_t o = 0;
+    pl.off_frame_ends = o; o = align_up(o + n_frames * 8, 256);
+    pl.off_seg_base = o;   o = align_up(o + (n_frames + 1) * 8, 256);
+    pl.off_seg_frame = o;  o = align_up(o + pl.max_segs * 4, 256);
+    pl.off_seg_entry = o;  o = align_up(o + pl.max_segs * 8, 256);
+    pl.off_seg_exit = o;   o = align_up(o + pl.max_segs * 8, 256);
+    pl.off_seg_count = o;  o = align_up(o + pl.max_segs * 4, 256);
+    pl.off_seg_b0 = o;     o = align_up(o + pl.max_segs * 8, 256);
+    pl.off_zero_begin = o;                                   // everything from here is zeroed per call
+    pl.off_changed = o;    o = align_up(o + 16, 256);
+    pl.off_anchors = o;    o = align_up(o + pl.n_tiles * 8, 256);
+    pl.off_widths = o;     o = align_up(o + n_frames * pl.nblocks + 16, 256);
+    pl.scratch_bytes = o;
+    return pl;
+}
+
+template <typename O, bool SGN>
+inline void unpack_launch_t(Launcher& L, const DecPlan& pl, const DecParams& p)
+{
+    if (pl.staged)
+        L.err = launch(prolix_unpack_kernel<O, SGN, true>, (u32)pl.n_tiles, DEC_NT, pl.smem_unpack, L.stream, p);
+    else
+        L.err = launch(prolix_unpack_kernel<O, SGN, false>, (u32)pl.n_tiles, DEC_NT, pl.smem_unpack, L.stream, p);
+    L.count();
+}
+template <bool SGN>
+inline void unpack_launch(Launcher& L, int out_dtype, const DecPlan& pl, const DecParams& p)
+{
+    switch (out_dtype) {
+    case DT_U8: unpack_launch_t<uint8_t, SGN>(L, pl, p); break;
+    case DT_U16: unpack_launch_t<uint16_t, SGN>(L, pl, p); break;
+    case DT_U32: unpack_launch_t<uint32_t, SGN>(L, pl, p); break;
+    case DT_U64: unpack_launch_t<uint64_t, SGN>(L, pl, p); break;
+    case DT_I8: unpack_launch_t<int8_t, SGN>(L, pl, p); break;
+    case DT_I16: unpack_launch_t<int16_t, SGN>(L, pl, p); break;
+    case DT_I32: unpack_launch_t<int32_t, SGN>(L, pl, p); break;
+    default: unpack_launch_t<int64_t, SGN>(L, pl, p); break;
+    }
+}
+
+// d_frame_ends == nullptr: recover the frame boundaries from the stream first (and report them in
+// d_frame_ends_out when given).  coop_grid: CTAs of the cooperative resolve kernel (all resident).
+inline void decode_async(Launcher& L, const void* d_payload, u64 payload_bytes, bool is_signed, u32 block,
+                         u64 n_values, u64 n_frames, const u64* d_frame_ends, u64* d_frame_ends_out,
+                         void* d_out, int out_dtype, u32* d_status, void* scratch, const DecPlan& pl,
+                         u32 coop_grid)
+{
+    L.err = cudaSuccess;
+    unsigned char* sc = (unsigned char*)scratch;
+    DecParams p;
+    p.payload = (const u32*)d_payload;
+    p.payload_bytes = payload_bytes;
+    p.block = block;
+    p.n_values = n_values;
+    p.n_frames = n_frames;
+    p.nblocks = pl.nblocks;
+    p.last_cnt = pl.last_cnt;
+    p.is_signed = is_signed ? 1 : 0;
+    p.seg_bytes = pl.seg_bytes;
+    p.warm_bytes = pl.warm_bytes;
+    p.max_segs = pl.max_segs;
+    p.seg_base = (u64*)(sc + pl.off_seg_base);
+    p.seg_frame = (u32*)(sc + pl.off_seg_frame);
+    p.seg_entry = (u64*)(sc + pl.off_seg_entry);
+    p.seg_exit = (u64*)(sc + pl.off_seg_exit);
+    p.seg_count = (u32*)(sc + pl.off_seg_count);
+    p.seg_b0 = (u64*)(sc + pl.off_seg_b0);
+    p.changed = (u32*)(sc + pl.off_changed);
+    p.widths = sc + pl.off_widths;
+    p.anchors = (u64*)(sc + pl.off_anchors);
+    p.tile_blocks = DEC_TB;
+    p.tiles_per_frame = pl.tiles_per_frame;
+    p.out = d_out;
+    p.status = d_status;
+    cudaMemsetAsync(d_status, 0, sizeof(u32), L.stream);
+    cudaMemsetAsync(sc + pl.off_zero_begin, 0, pl.scratch_bytes - pl.off_zero_begin, L.stream);
+    if (d_frame_ends == nullptr) {
+        u64* fe = d_frame_ends_out ? d_frame_ends_out : (u64*)(sc + pl.off_frame_ends);
+        if (n_frames == 1) {
+            // a single frame ends where the payload ends; nothing to search for
+            L.err = launch(prolix_single_frame_kernel, 1u, 32u, 0, L.stream, fe, payload_bytes);
+        } else {
+            L.err = launch(prolix_find_frames_kernel, 1u, 32u, 0, L.stream, p, fe);
+        }
+        L.count();
+        if (L.err != cudaSuccess) return;
+        d_frame_ends = fe;
+    }
+    p.frame_ends = d_frame_ends;
+    L.err = launch(prolix_segments_kernel<SEGTAB_NT>, 1u, (u32)SEGTAB_NT, 0, L.stream, p);
+    L.count();
+    if (L.err != cudaSuccess) return;
+    const u32 walk_grid = (u32)div_up(pl.max_segs, WALK_NT);
+    L.err = launch(prolix_walk_kernel<WALK_NT>, walk_grid, (u32)WALK_NT, 0, L.stream, p);
+    L.count();
+    if (L.err != cudaSuccess) return;
+    L.err = launch_coop(prolix_resolve_kernel<RESOLVE_NT>, coop_grid, (u32)RESOLVE_NT, 0, L.stream, p);
+    L.count();
+    if (L.err != cudaSuccess) return;
+    L.err = launch(prolix_emit_kernel<WALK_NT>, walk_grid, (u32)WALK_NT, 0, L.stream, p);
+    L.count();
+    if (L.err != cudaSuccess) return;
+    if (is_signed) unpack_launch<true>(L, out_dtype, pl, p);
+    else unpack_launch<false>(L, out_dtype, pl, p);
 }
 
 }  // namespace trpx

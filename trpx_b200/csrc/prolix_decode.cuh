@@ -1,4 +1,557 @@
+// prolix_decode.cuh -- PROLIX decoder for sm_100a.
+//
+// Replaces Terse::prolix(Iterator) (reference include/Terse.hpp:352-389), the header decode
+// (:361-372), Bit_range::get_range (include/Bit_pointer.hpp:742-792) and f_find_terse_frame
+// (Terse.hpp:562-585).
+//
+// The reference decodes serially because block b+1's header sits wherever block b ended.  Here the
+// chain is broken in two stages:
+//
+//   P1  header-state resolution.  Every frame is cut into fixed-size byte segments.  One thread per
+//       segment first walks the headers of the PREVIOUS segment speculatively ("warm-up": a walk
+//       started at a wrong bit self-synchronises with the true chain, because an explicit header
+//       resets the width and runs of '1' headers sit at a constant stride), then walks its own
+//       segment for real, recording entry state, exit state and block count.  A cooperative kernel
+//       then checks entry(j) == exit(j-1) for every segment and re-walks the ones that disagree until
+//       a whole sweep changes nothing -- at that point every entry state is EXACT by induction from
+//       the frame start, however adversarial the stream.  An exclusive scan of the block counts gives
+//       each segment its first block index; a last walk writes one width byte per block plus the bit
+//       position of every P2 tile.
+//   P2  unpack.  With widths known, block offsets inside a tile are a prefix sum (the mirror of the
+//       encoder's K3); each thread extracts whole blocks (uniform width), values are staged in
+//       shared memory and leave with one TMA bulk store per tile.
 #pragma once
+
 #include "simt.cuh"
+
 namespace trpx {
+
+struct DecParams {
+    const u32* payload;     // 16-byte aligned; readable up to the next multiple of 8 bytes
+    u64 payload_bytes;
+    u32 block;              // values per block
+    u64 n_values;           // values per frame
+    u64 n_frames;
+    u64 nblocks;            // blocks per frame
+    u32 last_cnt;           // values in a frame's last block
+    u32 is_signed;
+    const u64* frame_ends;  // [n_frames] end byte offsets
+    // P1 segment tables
+    u32 seg_bytes;          // segment size
+    u32 warm_bytes;         // speculative warm-up length before the segment (clipped at the frame start)
+    u64 max_segs;
+    u64* seg_base;          // [n_frames + 1] first segment of each frame
+    u32* seg_frame;         // [max_segs]
+    u64* seg_entry;         // [max_segs] (pos << 8) | width, frame-relative bit of the first header
+    u64* seg_exit;          // [max_segs]
+    u32* seg_count;         // [max_segs] headers that start inside the segment
+    u64* seg_b0;            // [max_segs] index of the segment's first block inside its frame
+    u32* changed;           // [3] rotating sweep flags of the fix-up loop (zeroed)
+    // P1 -> P2
+    unsigned char* widths;  // [n_frames * nblocks], zeroed
+    u64* anchors;           // [n_frames * tiles_per_frame] frame-relative bit of each tile's first header
+    u32 tile_blocks;
+    u64 tiles_per_frame;
+    void* out;
+    u32* status;            // [1]
+};
+
+constexpr u32 DEC_MALFORMED = 4;   // == TRPX_ERR_MALFORMED
+
+// ------------------------------------------------------------------ bit access
+// >= 33 valid bits of the stream starting at absolute bit `abit`
+TRPX_DEVICE u64 peek_bits(const u32* payload, u64 n_words, u64 abit)
+{
+    const u64 wi = abit >> 5;
+    const u32 lo = wi < n_words ? payload[wi] : 0u;
+    const u32 hi = wi + 1 < n_words ? payload[wi + 1] : 0u;
+    return (((u64)hi << 32) | lo) >> (abit & 31);
 }
+
+// Header at the window's bit 0 (Terse.hpp:361-372): returns header length, updates s.
+TRPX_DEVICE u32 decode_header(u64 win, u32& s)
+{
+    if (win & 1) return 1;
+    s = (u32)(win >> 1) & 7;
+    if (s != 7) return 4;
+    s += (u32)(win >> 4) & 3;
+    if (s != 10) return 6;
+    s += (u32)(win >> 6) & 63;
+    return 12;
+}
+
+TRPX_HD u64 pack_state(u64 pos, u32 s) { return (pos << 8) | (u64)s; }
+TRPX_HD u64 state_pos(u64 st) { return st >> 8; }
+TRPX_HD u32 state_s(u64 st) { return (u32)(st & 0xff); }
+
+// A walker's view of the stream: two consecutive 64-bit words cached in registers, so that a header
+// step usually needs no load at all and otherwise exactly one (the walk only moves forward).
+struct StreamWindow {
+    const u64* q;
+    u64 n_q, qi, q0, q1;
+    TRPX_DEVICE void init(const u32* payload, u64 n_words)
+    {
+        q = (const u64*)payload; n_q = (n_words + 1) >> 1; qi = ~0ull - 1; q0 = 0; q1 = 0;
+    }
+    TRPX_DEVICE u64 at(u64 i) const { return i < n_q ? q[i] : 0ull; }
+    TRPX_DEVICE u64 peek(u64 abit)          // 64 valid bits starting at absolute bit `abit`
+    {
+        const u64 i = abit >> 6;
+        const u32 sh = (u32)(abit & 63);
+        if (i != qi) {
+            q0 = (i == qi + 1) ? q1 : at(i);
+            q1 = at(i + 1);
+            qi = i;
+        }
+        return sh ? (q0 >> sh) | (q1 << (64 - sh)) : q0;
+    }
+};
+
+// Walk block headers from (pos, s) while pos < stop; all positions are bits relative to the frame,
+// base_bit is the frame's first bit in the payload.  Returns the number of headers visited.
+// Runs of '1' headers with width 0 (all-zero blocks, 1 bit each) are skipped a word at a time.
+struct NoSink {
+    TRPX_DEVICE void block(u64, u64, u32) {}
+    TRPX_DEVICE void zeros(u64, u64, u64) {}
+};
+template <class Sink>
+TRPX_DEVICE u64 walk_headers(const u32* payload, u64 n_words, u64 base_bit, u32 block, u64& pos, u32& s,
+                             u64 stop, Sink& sink)
+{
+    u64 n = 0;
+    StreamWindow sw;
+    sw.init(payload, n_words);
+    while (pos < stop) {
+        const u64 win = sw.peek(base_bit + pos);
+        if (s == 0 && (win & 1)) {
+            u64 run = (u64)ffs64(~win | (1ull << 63)) - 1;       // consecutive '1' headers (<= 63)
+            if (run > stop - pos) run = stop - pos;
+            sink.zeros(n, pos, run);
+            n += run;
+            pos += run;
+            continue;
+        }
+        const u32 hl = decode_header(win, s);
+        sink.block(n, pos, s);
+        pos += hl + (u64)s * block;
+        ++n;
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------ D0: segment table
+// nseg(f) = ceil(bytes_f / seg_bytes); seg_base = exclusive scan; seg_frame[j] = f.  One CTA.
+template <int NT>
+TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_segments_kernel(DecParams p)
+{
+    TRPX_SHARED u64 sm_tot[NT / 32];
+    TRPX_SHARED u64 sm_run;
+    const u32 t = tid(), lane = t & 31, warp = t >> 5;
+    if (t == 0) sm_run = 0;
+    sync_block();
+    for (u64 f0 = 0; f0 < p.n_frames; f0 += NT) {
+        const u64 f = f0 + t;
+        u64 nseg = 0;
+        if (f < p.n_frames) {
+            const u64 e = p.frame_ends[f], b = f ? p.frame_ends[f - 1] : 0;
+            if (e <= b || e > p.payload_bytes) atomic_max(p.status, DEC_MALFORMED);
+            else nseg = div_up(e - b, p.seg_bytes);
+        }
+        u64 incl = nseg;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            u64 v = shfl_up(incl, d);
+            if (lane >= (u32)d) incl += v;
+        }
+        if (lane == 31) sm_tot[warp] = incl;
+        sync_block();
+        u64 base = sm_run, total = 0;
+        for (int i = 0; i < NT / 32; ++i) {
+            u64 v = sm_tot[i];
+            if ((u32)i < warp) base += v;
+            total += v;
+        }
+        const u64 first = base + incl - nseg;
+        if (f < p.n_frames) {
+            p.seg_base[f] = first;
+            for (u64 i = 0; i < nseg && first + i < p.max_segs; ++i) p.seg_frame[first + i] = (u32)f;
+        }
+        sync_block();
+        if (t == 0) {
+            sm_run += total;
+            if (f0 + NT >= p.n_frames) p.seg_base[p.n_frames] = sm_run > p.max_segs ? p.max_segs : sm_run;
+        }
+        sync_block();
+    }
+}
+
+struct SegInfo { u64 frame, idx, base_bit, frame_bits, r0, r1; };
+TRPX_DEVICE SegInfo seg_info(const DecParams& p, u64 j)
+{
+    SegInfo g;
+    g.frame = p.seg_frame[j];
+    g.idx = j - p.seg_base[g.frame];
+    const u64 e = p.frame_ends[g.frame], b = g.frame ? p.frame_ends[g.frame - 1] : 0;
+    g.base_bit = b * 8;
+    g.frame_bits = (e - b) * 8;
+    g.r0 = g.idx * (u64)p.seg_bytes * 8;
+    g.r1 = g.r0 + (u64)p.seg_bytes * 8;
+    if (g.r1 > g.frame_bits) g.r1 = g.frame_bits;
+    return g;
+}
+
+// ------------------------------------------------------------------ D1: speculative + real walk
+template <int NT>
+TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_walk_kernel(DecParams p)
+{
+    const u64 j = (u64)bid() * NT + tid();
+    if (j >= p.seg_base[p.n_frames]) return;
+    const SegInfo g = seg_info(p, j);
+    const u64 n_words = (p.payload_bytes + 3) >> 2;
+    NoSink ns;
+    u64 pos = 0;
+    u32 s = 0;
+    if (g.idx > 0) {
+        // warm-up: start `warm_bytes` before the segment, pretending a header sits right there
+        const u64 back = (u64)p.warm_bytes * 8 < g.r0 ? (u64)p.warm_bytes * 8 : g.r0;
+        pos = g.r0 - back;
+        walk_headers(p.payload, n_words, g.base_bit, p.block, pos, s, g.r0, ns);
+    }
+    p.seg_entry[j] = pack_state(pos, s);
+    const u64 n = walk_headers(p.payload, n_words, g.base_bit, p.block, pos, s, g.r1, ns);
+    p.seg_exit[j] = pack_state(pos, s);
+    p.seg_count[j] = n > 0xffffffffull ? 0xffffffffu : (u32)n;
+}
+
+// ------------------------------------------------------------------ D2: verify / fix until stable, D3: scan
+// Cooperative launch (whole grid resident): grid_sync() is cooperative_groups' grid barrier on the
+// device and a block barrier in the single-CTA emulator run.
+template <int NT>
+TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_resolve_kernel(DecParams p)
+{
+    TRPX_SHARED u64 sm_tot[NT / 32];
+    TRPX_SHARED u64 sm_run;
+    const u32 t = tid(), lane = t & 31, warp = t >> 5;
+    const u64 n_segs = p.seg_base[p.n_frames];
+    const u64 n_words = (p.payload_bytes + 3) >> 2;
+    const u64 gthreads = (u64)nblocks() * NT, gtid = (u64)bid() * NT + t;
+    NoSink ns;
+    // ---- fix-up sweeps: entry(j) must equal exit(j-1) (same position; same width unless the header
+    // at that position is explicit).  Exact on exit: entry(0) is the frame start, and a sweep without
+    // a single rewrite means every segment was walked from its predecessor's recorded exit.
+    for (u32 sweep = 0;; ++sweep) {
+        // three rotating flags: sweep k raises flag k%3 and clears flag (k+1)%3, which nobody reads
+        // or raises until every CTA has passed this sweep's grid barrier
+        u32* flag = &p.changed[sweep % 3];
+        if (gtid == 0) p.changed[(sweep + 1) % 3] = 0;
+        for (u64 j = gtid; j < n_segs; j += gthreads) {
+            const SegInfo g = seg_info(p, j);
+            if (g.idx == 0) continue;
+            const u64 want = ld_relaxed(&p.seg_exit[j - 1]), have = p.seg_entry[j];
+            bool same = want == have;
+            if (!same && state_pos(want) == state_pos(have))
+                same = (peek_bits(p.payload, n_words, g.base_bit + state_pos(want)) & 1) == 0;
+            if (same) continue;
+            u64 pos = state_pos(want);
+            u32 s = state_s(want);
+            p.seg_entry[j] = want;
+            const u64 n = walk_headers(p.payload, n_words, g.base_bit, p.block, pos, s, g.r1, ns);
+            st_relaxed(&p.seg_exit[j], pack_state(pos, s));
+            p.seg_count[j] = n > 0xffffffffull ? 0xffffffffu : (u32)n;
+            atomic_or(flag, 1u);
+        }
+        grid_sync();
+        const u32 any = ld_relaxed(flag);
+        if (!any) break;
+        if (sweep > (1u << 22)) trap();
+    }
+    // ---- per-frame exclusive scan of the block counts (one CTA per frame, frames strided)
+    for (u64 f = bid(); f < p.n_frames; f += nblocks()) {
+        const u64 first = p.seg_base[f], nseg = p.seg_base[f + 1] - first;
+        if (t == 0) sm_run = 0;
+        sync_block();
+        for (u64 i0 = 0; i0 < nseg; i0 += NT) {
+            const u64 i = i0 + t;
+            const u64 c = i < nseg ? p.seg_count[first + i] : 0;
+            u64 incl = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                u64 v = shfl_up(incl, d);
+                if (lane >= (u32)d) incl += v;
+            }
+            if (lane == 31) sm_tot[warp] = incl;
+            sync_block();
+            u64 base = sm_run, total = 0;
+            for (int k = 0; k < NT / 32; ++k) {
+                u64 v = sm_tot[k];
+                if ((u32)k < warp) base += v;
+                total += v;
+            }
+            if (i < nseg) p.seg_b0[first + i] = base + incl - c;
+            sync_block();
+            if (t == 0) sm_run += total;
+            sync_block();
+        }
+        if (t == 0 && sm_run < p.nblocks) atomic_max(p.status, DEC_MALFORMED);   // stream ends early
+        sync_block();
+    }
+}
+
+// ------------------------------------------------------------------ D4: emit widths + tile anchors
+struct EmitSink {
+    const DecParams* p;
+    u64 frame, b0;          // frame index, first block index of the segment
+    u32 pend, pend_mask;    // up to 4 widths waiting to leave as one 32-bit store
+    u64 pend_word;          // word index of the pending group in the whole widths array
+    u32 bad;
+    TRPX_DEVICE void flush()
+    {
+        if (!pend_mask) return;
+        if (pend_mask == 0xF) {
+            ((u32*)p->widths)[pend_word] = pend;                  // group entirely ours
+        } else {                                                  // shared with a neighbour: bytes
+            for (int k = 0; k < 4; ++k)
+                if (pend_mask >> k & 1) p->widths[pend_word * 4 + k] = (unsigned char)(pend >> (8 * k));
+        }
+        pend = 0; pend_mask = 0;
+    }
+    TRPX_DEVICE void note_tile(u64 b, u64 pos)
+    {
+        if (b % p->tile_blocks == 0) p->anchors[frame * p->tiles_per_frame + b / p->tile_blocks] = pos;
+    }
+    TRPX_DEVICE void block(u64 k, u64 pos, u32 s)
+    {
+        const u64 b = b0 + k;
+        if (b >= p->nblocks) return;                              // padding bits after the last block
+        if (s > 65) bad = 1;
+        note_tile(b, pos);
+        if (s == 0) return;                                       // widths are pre-zeroed
+        const u64 gi = frame * p->nblocks + b, wi = gi >> 2;
+        if (pend_mask && wi != pend_word) flush();
+        pend_word = wi;
+        pend |= s << (8 * (u32)(gi & 3));
+        pend_mask |= 1u << (gi & 3);
+        if ((gi & 3) == 3) flush();
+    }
+    TRPX_DEVICE void zeros(u64 k, u64 pos, u64 run)
+    {
+        // only tile anchors can fall inside a run of empty blocks
+        u64 b = b0 + k;
+        const u64 end = b + run < p->nblocks ? b + run : p->nblocks;
+        u64 tb = div_up(b, p->tile_blocks) * p->tile_blocks;
+        for (; tb < end; tb += p->tile_blocks)
+            p->anchors[frame * p->tiles_per_frame + tb / p->tile_blocks] = pos + (tb - b);
+    }
+};
+
+template <int NT>
+TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_emit_kernel(DecParams p)
+{
+    const u64 j = (u64)bid() * NT + tid();
+    if (j >= p.seg_base[p.n_frames]) return;
+    const SegInfo g = seg_info(p, j);
+    const u64 n_words = (p.payload_bytes + 3) >> 2;
+    const u64 b0 = p.seg_b0[j];
+    if (b0 >= p.nblocks) return;
+    EmitSink sink;
+    sink.p = &p; sink.frame = g.frame; sink.b0 = b0; sink.pend = 0; sink.pend_mask = 0; sink.pend_word = 0; sink.bad = 0;
+    const u64 st = p.seg_entry[j];
+    u64 pos = state_pos(st);
+    u32 s = state_s(st);
+    walk_headers(p.payload, n_words, g.base_bit, p.block, pos, s, g.r1, sink);
+    sink.flush();
+    if (sink.bad) atomic_max(p.status, DEC_MALFORMED);
+}
+
+// ------------------------------------------------------------------ D5 (P2): unpack
+struct BitSource {
+    const u32* payload;
+    u64 n_words, wi;
+    u64 acc;
+    u32 nb;
+    TRPX_DEVICE void init(const u32* pl, u64 nw, u64 abit)
+    {
+        payload = pl; n_words = nw; wi = abit >> 5;
+        const u32 sh = (u32)(abit & 31);
+        acc = (u64)(wi < n_words ? ld_stream(&payload[wi]) : 0u) >> sh;
+        nb = 32 - sh;
+        ++wi;
+    }
+    TRPX_DEVICE u32 get(u32 n)      // n in [0, 32]
+    {
+        if (nb < n) {
+            acc |= (u64)(wi < n_words ? ld_stream(&payload[wi]) : 0u) << nb;
+            nb += 32;
+            ++wi;
+        }
+        const u32 v = n == 32 ? (u32)acc : (u32)acc & ((1u << n) - 1);
+        acc >>= n;
+        nb -= n;
+        return v;
+    }
+    TRPX_DEVICE u64 get_wide(u32 s)  // s in [1, 73]; returns the low 64 bits
+    {
+        u64 v = get(s < 32 ? s : 32);
+        if (s > 32) v |= (u64)get(s - 32 < 32 ? s - 32 : 32) << 32;
+        if (s > 64) (void)get(s - 64);                            // bits above 64 repeat the sign
+        return v;
+    }
+};
+
+// Bit_range::get_range semantics (Bit_pointer.hpp:742-792): sign-extend signed streams from bit
+// s-1; a block wider than the output type is clamped to the type's range, else truncated.
+template <typename O, bool SGN>
+TRPX_DEVICE O convert_value(u64 raw, u32 s)
+{
+    constexpr u32 WO = 8 * sizeof(O);
+    constexpr bool OS = O(-1) < O(0);
+    u64 v = raw;
+    if (SGN && s < 64 && ((v >> (s - 1)) & 1)) v |= ~0ull << s;
+    if (s > WO) {
+        if (!OS) {
+            const u64 hi = WO == 64 ? ~0ull : ((1ull << WO) - 1);
+            const u64 x = SGN ? ((i64)v < 0 ? 0ull : v) : v;
+            v = x > hi ? hi : x;
+        } else {
+            const i64 hi = (i64)((1ull << (WO - 1)) - 1), lo = -hi - 1;
+            const i64 x = SGN ? (i64)v : (v > 0x7fffffffffffffffull ? 0x7fffffffffffffffll : (i64)v);
+            v = (u64)(x < lo ? lo : (x > hi ? hi : x));
+        }
+    }
+    return (O)v;
+}
+
+constexpr int DEC_NT = 256;
+constexpr int DEC_RB = 4;                               // blocks per thread in the tile scan
+constexpr int DEC_TB = DEC_NT * DEC_RB;                 // blocks per P2 tile
+
+TRPX_HD u32 header_len(u32 s, u32 prev) { return s == prev ? 1u : (s < 7 ? 4u : (s < 10 ? 6u : 12u)); }
+
+// STAGED: block == 12, 16-byte aligned frames -> values leave through shared memory + TMA store.
+// otherwise: each thread stores its block's values straight to global memory.
+template <typename O, bool SGN, bool STAGED>
+TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(DEC_NT, 1) prolix_unpack_kernel(DecParams p)
+{
+    constexpr int NT = DEC_NT;
+    TRPX_DYN_SMEM(sm);
+    u32* sm_warp_tot = (u32*)sm;                                  // 32 u32
+    unsigned char* wsm = sm + 128;                                // DEC_TB + 1 widths (+ pad)
+    u32* tp = (u32*)(sm + 128 + DEC_TB + 16);                     // DEC_TB data offsets (bits, tile-relative)
+    O* stage = (O*)(sm + 128 + DEC_TB + 16 + DEC_TB * 4);         // DEC_TB * 12 values (STAGED only)
+    const u32 t = tid(), lane = t & 31, warp = t >> 5;
+    const u64 tile = bid();
+    const u64 f = tile / p.tiles_per_frame, tif = tile % p.tiles_per_frame;
+    const u64 b0 = tif * DEC_TB;
+    const u64 nb_tile = p.nblocks - b0 < (u64)DEC_TB ? p.nblocks - b0 : (u64)DEC_TB;
+    const unsigned char* wrow = p.widths + f * p.nblocks;
+    const u64 n_words = (p.payload_bytes + 3) >> 2;
+    const u64 base_bit = (f ? p.frame_ends[f - 1] : 0) * 8;
+    const u64 frame_bits = (p.frame_ends[f] - (f ? p.frame_ends[f - 1] : 0)) * 8;
+    const u64 anchor = p.anchors[tile];
+
+    // widths of blocks b0-1 .. b0+nb_tile-1 -> wsm[0 .. nb_tile]
+    for (u32 i = t; i <= nb_tile; i += NT) wsm[i] = (i == 0) ? (b0 ? wrow[b0 - 1] : 0) : wrow[b0 + i - 1];
+    sync_block();
+
+    // lengths of my DEC_RB consecutive blocks -> tile-relative data offsets
+    u32 hl[DEC_RB], len = 0;
+#pragma unroll
+    for (int i = 0; i < DEC_RB; ++i) {
+        const u32 k = t * DEC_RB + i;
+        hl[i] = 0;
+        if (k < nb_tile) {
+            const u32 s = wsm[k + 1];
+            const u32 cnt = (b0 + k + 1 == p.nblocks) ? p.last_cnt : p.block;
+            hl[i] = header_len(s, wsm[k]);
+            len += hl[i] + s * cnt;
+        }
+    }
+    u32 incl = len;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u32 v = shfl_up(incl, d);
+        if (lane >= (u32)d) incl += v;
+    }
+    if (lane == 31) sm_warp_tot[warp] = incl;
+    sync_block();
+    u32 off = incl - len, total = 0;
+    for (int i = 0; i < NT / 32; ++i) {
+        const u32 v = sm_warp_tot[i];
+        if ((u32)i < warp) off += v;
+        total += v;
+    }
+#pragma unroll
+    for (int i = 0; i < DEC_RB; ++i) {
+        const u32 k = t * DEC_RB + i;
+        if (k < nb_tile) {
+            const u32 s = wsm[k + 1];
+            const u32 cnt = (b0 + k + 1 == p.nblocks) ? p.last_cnt : p.block;
+            tp[k] = off + hl[i];
+            off += hl[i] + s * cnt;
+        }
+    }
+    if (t == 0 && anchor + total > frame_bits) atomic_max(p.status, DEC_MALFORMED);
+    sync_block();
+
+    // unpack: thread t takes blocks t, t+NT, ... (neighbouring lanes read neighbouring bits)
+    O* outf = (O*)p.out + f * p.n_values;
+    for (u32 k = t; k < nb_tile; k += NT) {
+        const u32 s = wsm[k + 1];
+        const u32 cnt = (b0 + k + 1 == p.nblocks) ? p.last_cnt : p.block;
+        O* dst = STAGED ? stage + (size_t)k * 12 : outf + (b0 + k) * p.block;
+        if (s == 0) {
+            for (u32 i = 0; i < cnt; ++i) dst[i] = (O)0;
+            continue;
+        }
+        BitSource src;
+        src.init(p.payload, n_words, base_bit + anchor + tp[k]);
+        if (s <= 32) {
+            for (u32 i = 0; i < cnt; ++i) dst[i] = convert_value<O, SGN>(src.get(s), s);
+        } else {
+            for (u32 i = 0; i < cnt; ++i) dst[i] = convert_value<O, SGN>(src.get_wide(s), s);
+        }
+    }
+    if (STAGED) {
+        fence_async_smem();
+        sync_block();
+        if (t == 0) {
+            const u64 v0 = b0 * 12;
+            const u64 nv = p.n_values - v0 < (u64)DEC_TB * 12 ? p.n_values - v0 : (u64)DEC_TB * 12;
+            bulk_s2g(outf + v0, stage, (u32)(nv * sizeof(O)));
+            bulk_commit();
+            bulk_wait_read0();
+        }
+    }
+}
+
+// ------------------------------------------------------------------ frame sizes unknown
+// The .trpx header stores only the total payload size (Terse.hpp:459), so a foreign multi-frame
+// payload has to be walked to find where each frame ends (Terse.hpp:562-585).  Round-1 version: one
+// thread walks the chain (correct for any stream; slow -- DESIGN.md lists the parallel replacement).
+TRPX_KERNEL void prolix_single_frame_kernel(u64* frame_ends_out, u64 payload_bytes)
+{
+    if (bid() == 0 && tid() == 0) frame_ends_out[0] = payload_bytes;
+}
+
+TRPX_KERNEL void prolix_find_frames_kernel(DecParams p, u64* frame_ends_out)
+{
+    if (bid() != 0 || tid() != 0) return;
+    const u64 n_words = (p.payload_bytes + 3) >> 2;
+    const u64 total_bits = p.payload_bytes * 8;
+    u64 start = 0;                                                // byte offset of the frame
+    for (u64 f = 0; f < p.n_frames; ++f) {
+        u64 pos = 0;
+        u32 s = 0;
+        for (u64 b = 0; b < p.nblocks; ++b) {
+            if (start * 8 + pos >= total_bits) { atomic_max(p.status, DEC_MALFORMED); break; }
+            const u64 win = peek_bits(p.payload, n_words, start * 8 + pos);
+            const u32 hl = decode_header(win, s);
+            pos += hl + (u64)s * (b + 1 == p.nblocks ? p.last_cnt : p.block);
+        }
+        start += 1 + (pos >> 3);
+        if (start > p.payload_bytes) { atomic_max(p.status, DEC_MALFORMED); start = p.payload_bytes; }
+        frame_ends_out[f] = start;
+    }
+}
+
+}  // namespace trpx

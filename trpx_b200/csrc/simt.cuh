@@ -17,6 +17,7 @@
 #include "emu.hpp"
 #else
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #endif
 
 namespace trpx {
@@ -157,8 +158,21 @@ template <typename... KArgs, typename... Args>
 inline cudaError_t launch(void (*kern)(KArgs...), u32 grid, u32 block, size_t smem, cudaStream_t st,
                           Args... args)
 {
+    if (smem > 48 * 1024) {   // opt in to large dynamic shared memory (up to 227 KB per CTA on sm_100a)
+        cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
     kern<<<grid, block, smem, st>>>(KArgs(args)...);
     return cudaGetLastError();
+}
+
+// grid-wide barrier of a cooperative launch (all CTAs resident by construction)
+TRPX_DEVICE void grid_sync() { cooperative_groups::this_grid().sync(); }
+template <typename P>
+inline cudaError_t launch_coop(void (*kern)(P), u32 grid, u32 block, size_t smem, cudaStream_t st, P arg)
+{
+    void* kargs[] = {(void*)&arg};
+    return cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(block), kargs, smem, st);
 }
 
 #else
@@ -263,6 +277,14 @@ inline cudaError_t launch(void (*kern)(KArgs...), u32 grid, u32 block, size_t sm
                           Args... args)
 {
     ::emu::run_grid(grid, block, smem, [&]() { kern(KArgs(args)...); });
+    return cudaSuccess;
+}
+// the emulator runs the blocks of a grid one after another, so a "cooperative" launch is one CTA
+inline void grid_sync() { ::emu::sync_block(); }
+template <typename P>
+inline cudaError_t launch_coop(void (*kern)(P), u32, u32 block, size_t smem, cudaStream_t, P arg)
+{
+    ::emu::run_grid(1, block, smem, [&]() { kern(arg); });
     return cudaSuccess;
 }
 #endif

@@ -1,0 +1,450 @@
+// trpx_api.cu -- the C ABI of libtrpx_b200.so (include/trpx_b200.h): contexts, lanes (stream +
+// scratch + staging), the host-pointer pipelines (H2D -> kernels -> D2H over several lanes) and the
+// device-pointer entry points.  All arithmetic of the codec is in terse_encode.cuh /
+// prolix_decode.cuh; there is no host implementation of it anywhere in this library.
+#include "../../include/trpx_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "codec_launch.cuh"
+
+using namespace trpx;
+
+namespace {
+
+constexpr int N_LANES = 3;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct Lane {
+    cudaStream_t stream = nullptr;
+    DevBuf enc_scratch, dec_scratch;   // look-back descriptors / P1 tables
+    DevBuf d_in, d_out, d_ends;        // staging of the host-pointer flavours
+    u32* d_small = nullptr;            // [0] prolix_bits, [1] status
+    u32* h_small = nullptr;            // pinned mirror
+    u64* h_ends = nullptr;             // pinned copy of frame ends
+    size_t h_ends_cap = 0;
+};
+
+}  // namespace
+
+struct trpx_ctx {
+    int device = 0;
+    int sm_count = 0;
+    Lane lanes[N_LANES];
+    u64 launches = 0;
+    std::string last_error;
+    std::mutex mu;
+    u32 seg_bytes = 16384, warm_bytes = 8192;
+    size_t batch_bytes = 256u << 20;   // raw pixel bytes per pipeline batch of the host flavours
+    u32 coop_grid = 0;
+};
+
+namespace {
+
+bool cuda_ok(trpx_ctx* c, cudaError_t e, const char* what)
+{
+    if (e == cudaSuccess) return true;
+    if (c) c->last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return false;
+}
+
+bool ensure(trpx_ctx* c, DevBuf& b, size_t bytes)
+{
+    if (b.cap >= bytes) return true;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 8 + 4096;
+    if (!cuda_ok(c, cudaMalloc(&b.p, want), "cudaMalloc")) return false;
+    b.cap = want;
+    return true;
+}
+
+bool ensure_host_ends(trpx_ctx* c, Lane& l, size_t n)
+{
+    if (l.h_ends_cap >= n) return true;
+    if (l.h_ends) cudaFreeHost(l.h_ends);
+    l.h_ends = nullptr;
+    l.h_ends_cap = 0;
+    if (!cuda_ok(c, cudaMallocHost((void**)&l.h_ends, (n + 1024) * sizeof(u64)), "cudaMallocHost")) return false;
+    l.h_ends_cap = n + 1024;
+    return true;
+}
+
+u32 env_u32(const char* name, u32 dflt)
+{
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    return (u32)strtoul(v, nullptr, 10);
+}
+
+u32 enc_ctas_per_sm(trpx_ctx* c, int dtype, const EncPlan& pl)
+{
+    int n = 0;
+    const void* k = enc_kernel(dtype, pl.fast);
+    if (pl.smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, pl.fast ? ENC_NT : GEN_NT, pl.smem);
+    if (e != cudaSuccess || n < 1) { cudaGetLastError(); n = 1; }
+    (void)c;
+    return (u32)n;
+}
+
+Launcher make_launcher(trpx_ctx* c, cudaStream_t s)
+{
+    Launcher L;
+    L.stream = s;
+    L.sm_count = (u32)c->sm_count;
+    L.launches = &c->launches;
+    L.err = cudaSuccess;
+    return L;
+}
+
+int status_of_device_word(u32 w) { return w == 0 ? TRPX_OK : (int)w; }
+
+}  // namespace
+
+extern "C" {
+
+int trpx_abi_version(void) { return TRPX_ABI_VERSION; }
+
+const char* trpx_strerror(int s)
+{
+    switch (s) {
+    case TRPX_OK: return "ok";
+    case TRPX_ERR_BAD_ARG: return "bad argument";
+    case TRPX_ERR_CAPACITY: return "output buffer too small";
+    case TRPX_ERR_CUDA: return "CUDA error";
+    case TRPX_ERR_MALFORMED: return "malformed TERSE payload";
+    case TRPX_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU path)";
+    case TRPX_ERR_NOMEM: return "out of memory";
+    default: return "unknown status";
+    }
+}
+
+size_t trpx_dtype_size(int dtype) { return dtype_size(dtype); }
+int trpx_dtype_is_signed(int dtype) { return dtype_signed(dtype) ? 1 : 0; }
+
+size_t trpx_max_compressed_bytes(size_t n_values, int dtype, unsigned block, size_t n_frames)
+{
+    const size_t sz = dtype_size(dtype);
+    if (!sz || !block) return 0;
+    const size_t w = 8 * sz + (dtype_signed(dtype) ? 1 : 0);
+    const size_t nblocks = (n_values + block - 1) / block;
+    const size_t per_frame = (12 * nblocks + n_values * w + 7) / 8 + 1;
+    return (per_frame * n_frames + 15 + 16) / 16 * 16;
+}
+
+int trpx_ctx_create(int device, trpx_ctx** out)
+{
+    if (!out) return TRPX_ERR_BAD_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return TRPX_ERR_NO_DEVICE; }
+    if (device < 0 || device >= n) return TRPX_ERR_BAD_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return TRPX_ERR_NO_DEVICE; }
+    trpx_ctx* c = new trpx_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    if (!cuda_ok(c, cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) { delete c; return TRPX_ERR_CUDA; }
+    c->sm_count = prop.multiProcessorCount;
+    if (!prop.cooperativeLaunch) { delete c; return TRPX_ERR_NO_DEVICE; }
+    for (int i = 0; i < N_LANES; ++i) {
+        Lane& l = c->lanes[i];
+        if (!cuda_ok(c, cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking), "cudaStreamCreate") ||
+            !cuda_ok(c, cudaMalloc((void**)&l.d_small, 64), "cudaMalloc") ||
+            !cuda_ok(c, cudaMallocHost((void**)&l.h_small, 64), "cudaMallocHost")) {
+            trpx_ctx_destroy(c);
+            return TRPX_ERR_NOMEM;
+        }
+    }
+    c->seg_bytes = env_u32("TRPX_SEG_BYTES", c->seg_bytes);
+    c->warm_bytes = env_u32("TRPX_WARM_BYTES", c->warm_bytes);
+    c->batch_bytes = (size_t)env_u32("TRPX_BATCH_MB", (u32)(c->batch_bytes >> 20)) << 20;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)prolix_resolve_kernel<RESOLVE_NT>, RESOLVE_NT, 0) != cudaSuccess || occ < 1) {
+        cudaGetLastError();
+        occ = 1;
+    }
+    if (occ > 4) occ = 4;
+    c->coop_grid = (u32)(c->sm_count * occ);
+    *out = c;
+    return TRPX_OK;
+}
+
+void trpx_ctx_destroy(trpx_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (int i = 0; i < N_LANES; ++i) {
+        Lane& l = c->lanes[i];
+        if (l.stream) { cudaStreamSynchronize(l.stream); cudaStreamDestroy(l.stream); }
+        DevBuf* bufs[] = {&l.enc_scratch, &l.dec_scratch, &l.d_in, &l.d_out, &l.d_ends};
+        for (DevBuf* b : bufs)
+            if (b->p) cudaFree(b->p);
+        if (l.d_small) cudaFree(l.d_small);
+        if (l.h_small) cudaFreeHost(l.h_small);
+        if (l.h_ends) cudaFreeHost(l.h_ends);
+    }
+    delete c;
+}
+
+int trpx_ctx_device(const trpx_ctx* c) { return c ? c->device : -1; }
+const char* trpx_last_error(const trpx_ctx* c) { return c ? c->last_error.c_str() : ""; }
+int trpx_ctx_lanes(const trpx_ctx* c) { return c ? N_LANES : 0; }
+uint64_t trpx_ctx_launch_count(const trpx_ctx* c) { return c ? c->launches : 0; }
+size_t trpx_ctx_scratch_bytes(const trpx_ctx* c)
+{
+    size_t t = 0;
+    if (c)
+        for (int i = 0; i < N_LANES; ++i) {
+            const Lane& l = c->lanes[i];
+            t += l.enc_scratch.cap + l.dec_scratch.cap + l.d_in.cap + l.d_out.cap + l.d_ends.cap;
+        }
+    return t;
+}
+
+// ------------------------------------------------------------------------------ TERSE, device pointers
+int trpx_encode_device(trpx_ctx* c, int lane, const void* d_pixels, int dtype, size_t n_values,
+                       size_t n_frames, unsigned block, uint8_t* d_out, size_t out_capacity,
+                       uint64_t* d_frame_ends, uint32_t* d_prolix_bits, uint32_t* d_status, void* stream)
+{
+    if (!c) return TRPX_ERR_BAD_ARG;
+    if (lane < 0 || lane >= N_LANES || !d_pixels || !d_out || !d_frame_ends || !d_prolix_bits || !d_status ||
+        !dtype_size(dtype) || !block || !n_values || !n_frames)
+        return TRPX_ERR_BAD_ARG;
+    if (((uintptr_t)d_out & 15) || ((uintptr_t)d_pixels & (dtype_size(dtype) - 1))) return TRPX_ERR_BAD_ARG;
+    cudaSetDevice(c->device);
+    EncPlan pl = enc_plan(dtype, d_pixels, n_values, n_frames, block);
+    if (!pl.ok) { c->last_error = "unsupported geometry (block too large or too many tiles)"; return TRPX_ERR_BAD_ARG; }
+    Lane& l = c->lanes[lane];
+    if (!ensure(c, l.enc_scratch, pl.scratch_bytes)) return TRPX_ERR_NOMEM;
+    Launcher L = make_launcher(c, (cudaStream_t)stream);
+    encode_async(L, dtype, d_pixels, n_values, n_frames, block, d_out, out_capacity, (u64*)d_frame_ends,
+                 d_prolix_bits, d_status, l.enc_scratch.p, pl, enc_ctas_per_sm(c, dtype, pl));
+    if (!cuda_ok(c, L.err, "encode launch")) return TRPX_ERR_CUDA;
+    return TRPX_OK;
+}
+
+// ------------------------------------------------------------------------------ PROLIX, device pointers
+int trpx_decode_device(trpx_ctx* c, int lane, const uint8_t* d_payload, size_t payload_bytes, int is_signed,
+                       unsigned block, size_t n_values, size_t n_frames, const uint64_t* d_frame_ends,
+                       uint64_t* d_frame_ends_out, void* d_out, int out_dtype, uint32_t* d_status, void* stream)
+{
+    if (!c) return TRPX_ERR_BAD_ARG;
+    if (lane < 0 || lane >= N_LANES || !d_payload || !payload_bytes || !d_out || !d_status ||
+        !dtype_size(out_dtype) || !block || !n_values || !n_frames)
+        return TRPX_ERR_BAD_ARG;
+    if (is_signed && !dtype_signed(out_dtype)) return TRPX_ERR_BAD_ARG;      // Terse.hpp:356-357
+    if (((uintptr_t)d_payload & 15) || ((uintptr_t)d_out & (dtype_size(out_dtype) - 1))) return TRPX_ERR_BAD_ARG;
+    cudaSetDevice(c->device);
+    DecPlan pl = dec_plan(out_dtype, payload_bytes, n_values, n_frames, block, d_out, c->seg_bytes, c->warm_bytes);
+    if (!pl.ok) return TRPX_ERR_BAD_ARG;
+    Lane& l = c->lanes[lane];
+    if (!ensure(c, l.dec_scratch, pl.scratch_bytes)) return TRPX_ERR_NOMEM;
+    Launcher L = make_launcher(c, (cudaStream_t)stream);
+    decode_async(L, d_payload, payload_bytes, is_signed != 0, block, n_values, n_frames, (const u64*)d_frame_ends,
+                 (u64*)d_frame_ends_out, d_out, out_dtype, d_status, l.dec_scratch.p, pl, c->coop_grid);
+    if (!cuda_ok(c, L.err, "decode launch")) return TRPX_ERR_CUDA;
+    return TRPX_OK;
+}
+
+// ------------------------------------------------------------------------------ TERSE, host pointers
+// Frames are cut into batches of ~batch_bytes; batch b runs on lane b % N_LANES: H2D, encode, D2H of
+// (frame ends, prolix_bits, status), then -- once its size is known -- D2H of the payload straight to
+// its final place in `out`.  Up to N_LANES batches are in flight, so copies overlap kernels.
+int trpx_encode_host(trpx_ctx* c, const void* pixels, int dtype, size_t n_values, size_t n_frames, unsigned block,
+                     uint8_t* out, size_t out_capacity, size_t* frame_bytes, size_t* total_bytes,
+                     unsigned* prolix_bits)
+{
+    if (!c) return TRPX_ERR_BAD_ARG;
+    const size_t sz = dtype_size(dtype);
+    if (!pixels || !out || !sz || !block || !n_values || !n_frames) return TRPX_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> guard(c->mu);
+    cudaSetDevice(c->device);
+    const size_t frame_raw = n_values * sz;
+    size_t fpb = c->batch_bytes / (frame_raw ? frame_raw : 1);   // frames per batch
+    if (fpb < 1) fpb = 1;
+    if (fpb > n_frames) fpb = n_frames;
+    const size_t n_batches = (n_frames + fpb - 1) / fpb;
+
+    struct Pending { size_t f0, nf; bool active; };
+    Pending pend[N_LANES] = {};
+    size_t out_off = 0;
+    unsigned pb_max = 0;
+    int rc = TRPX_OK;
+
+    auto finish = [&](int li) -> int {
+        Lane& l = c->lanes[li];
+        Pending& q = pend[li];
+        if (!q.active) return TRPX_OK;
+        q.active = false;
+        if (!cuda_ok(c, cudaStreamSynchronize(l.stream), "encode batch")) return TRPX_ERR_CUDA;
+        if (l.h_small[1] != 0) return status_of_device_word(l.h_small[1]);
+        const size_t bytes = (size_t)l.h_ends[q.nf - 1];
+        if (out_off + bytes > out_capacity) return TRPX_ERR_CAPACITY;
+        if (!cuda_ok(c, cudaMemcpyAsync(out + out_off, l.d_out.p, bytes, cudaMemcpyDeviceToHost, l.stream), "D2H payload"))
+            return TRPX_ERR_CUDA;
+        if (frame_bytes)
+            for (size_t i = 0; i < q.nf; ++i) frame_bytes[q.f0 + i] = (size_t)(l.h_ends[i] - (i ? l.h_ends[i - 1] : 0));
+        if (l.h_small[0] > pb_max) pb_max = l.h_small[0];
+        out_off += bytes;
+        if (!cuda_ok(c, cudaStreamSynchronize(l.stream), "D2H payload")) return TRPX_ERR_CUDA;
+        return TRPX_OK;
+    };
+
+    for (size_t b = 0; b < n_batches && rc == TRPX_OK; ++b) {
+        const int li = (int)(b % N_LANES);
+        Lane& l = c->lanes[li];
+        rc = finish(li);
+        if (rc != TRPX_OK) break;
+        const size_t f0 = b * fpb, nf = (f0 + fpb <= n_frames) ? fpb : n_frames - f0;
+        const size_t cap = trpx_max_compressed_bytes(n_values, dtype, block, nf);
+        if (!ensure(c, l.d_in, nf * frame_raw + 16) || !ensure(c, l.d_out, cap) || !ensure(c, l.d_ends, nf * 8) ||
+            !ensure_host_ends(c, l, nf)) { rc = TRPX_ERR_NOMEM; break; }
+        EncPlan pl = enc_plan(dtype, l.d_in.p, n_values, nf, block);
+        if (!pl.ok) { c->last_error = "unsupported geometry (block too large or too many tiles)"; rc = TRPX_ERR_BAD_ARG; break; }
+        if (!ensure(c, l.enc_scratch, pl.scratch_bytes)) { rc = TRPX_ERR_NOMEM; break; }
+        if (!cuda_ok(c, cudaMemcpyAsync(l.d_in.p, (const uint8_t*)pixels + f0 * frame_raw, nf * frame_raw,
+                                        cudaMemcpyHostToDevice, l.stream), "H2D pixels")) { rc = TRPX_ERR_CUDA; break; }
+        Launcher L = make_launcher(c, l.stream);
+        encode_async(L, dtype, l.d_in.p, n_values, nf, block, l.d_out.p, cap, (u64*)l.d_ends.p, l.d_small, l.d_small + 1,
+                     l.enc_scratch.p, pl, enc_ctas_per_sm(c, dtype, pl));
+        if (!cuda_ok(c, L.err, "encode launch")) { rc = TRPX_ERR_CUDA; break; }
+        cudaMemcpyAsync(l.h_small, l.d_small, 8, cudaMemcpyDeviceToHost, l.stream);
+        cudaMemcpyAsync(l.h_ends, l.d_ends.p, nf * 8, cudaMemcpyDeviceToHost, l.stream);
+        pend[li] = Pending{f0, nf, true};
+    }
+    // drain in batch order
+    for (size_t k = 0; k < (size_t)N_LANES; ++k) {
+        const int li = (int)((n_batches + k) % N_LANES);
+        int r = finish(li);
+        if (rc == TRPX_OK) rc = r;
+    }
+    if (rc != TRPX_OK) {
+        for (int i = 0; i < N_LANES; ++i) cudaStreamSynchronize(c->lanes[i].stream);
+        return rc;
+    }
+    if (total_bytes) *total_bytes = out_off;
+    if (prolix_bits) *prolix_bits = pb_max;
+    return TRPX_OK;
+}
+
+// ------------------------------------------------------------------------------ PROLIX, host pointers
+int trpx_decode_host(trpx_ctx* c, const uint8_t* payload, size_t payload_bytes, int is_signed, unsigned block,
+                     size_t n_values, size_t total_frames, size_t first_frame, size_t n_frames,
+                     const size_t* frame_bytes, size_t* frame_bytes_out, void* out, int out_dtype)
+{
+    if (!c) return TRPX_ERR_BAD_ARG;
+    const size_t so = dtype_size(out_dtype);
+    if (!payload || !payload_bytes || !out || !so || !block || !n_values || !total_frames || !n_frames ||
+        first_frame + n_frames > total_frames)
+        return TRPX_ERR_BAD_ARG;
+    if (is_signed && !dtype_signed(out_dtype)) return TRPX_ERR_BAD_ARG;      // Terse.hpp:356-357
+    std::lock_guard<std::mutex> guard(c->mu);
+    cudaSetDevice(c->device);
+
+    // absolute end offsets of every frame
+    std::vector<u64> ends(total_frames);
+    if (frame_bytes) {
+        u64 acc = 0;
+        for (size_t f = 0; f < total_frames; ++f) { acc += frame_bytes[f]; ends[f] = acc; }
+        if (acc > payload_bytes) return TRPX_ERR_MALFORMED;
+    } else if (total_frames == 1) {
+        ends[0] = payload_bytes;
+    } else {
+        // the container does not store frame boundaries (Terse.hpp:459, :562-585): recover them on the device
+        Lane& l = c->lanes[0];
+        DecPlan pl = dec_plan(out_dtype, payload_bytes, n_values, total_frames, block, nullptr, c->seg_bytes, c->warm_bytes);
+        if (!pl.ok) return TRPX_ERR_BAD_ARG;
+        if (!ensure(c, l.d_in, payload_bytes + 16) || !ensure(c, l.d_ends, total_frames * 8)) return TRPX_ERR_NOMEM;
+        if (!cuda_ok(c, cudaMemsetAsync((uint8_t*)l.d_in.p + payload_bytes, 0, 16, l.stream), "memset") ||
+            !cuda_ok(c, cudaMemcpyAsync(l.d_in.p, payload, payload_bytes, cudaMemcpyHostToDevice, l.stream), "H2D payload"))
+            return TRPX_ERR_CUDA;
+        DecParams p{};
+        p.payload = (const u32*)l.d_in.p;
+        p.payload_bytes = payload_bytes;
+        p.block = block;
+        p.n_values = n_values;
+        p.n_frames = total_frames;
+        p.nblocks = pl.nblocks;
+        p.last_cnt = pl.last_cnt;
+        p.status = l.d_small + 1;
+        cudaMemsetAsync(l.d_small, 0, 8, l.stream);
+        Launcher L = make_launcher(c, l.stream);
+        L.err = launch(prolix_find_frames_kernel, 1u, 32u, 0, l.stream, p, (u64*)l.d_ends.p);
+        L.count();
+        if (!cuda_ok(c, L.err, "find frames launch")) return TRPX_ERR_CUDA;
+        cudaMemcpyAsync(ends.data(), l.d_ends.p, total_frames * 8, cudaMemcpyDeviceToHost, l.stream);
+        cudaMemcpyAsync(l.h_small, l.d_small, 8, cudaMemcpyDeviceToHost, l.stream);
+        if (!cuda_ok(c, cudaStreamSynchronize(l.stream), "find frames")) return TRPX_ERR_CUDA;
+        if (l.h_small[1] != 0) return status_of_device_word(l.h_small[1]);
+    }
+    if (frame_bytes_out)
+        for (size_t f = 0; f < total_frames; ++f) frame_bytes_out[f] = (size_t)(ends[f] - (f ? ends[f - 1] : 0));
+
+    const size_t frame_raw = n_values * so;
+    size_t fpb = c->batch_bytes / (frame_raw ? frame_raw : 1);
+    if (fpb < 1) fpb = 1;
+    if (fpb > n_frames) fpb = n_frames;
+    const size_t n_batches = (n_frames + fpb - 1) / fpb;
+    bool active[N_LANES] = {};
+    int rc = TRPX_OK;
+
+    auto finish = [&](int li) -> int {
+        Lane& l = c->lanes[li];
+        if (!active[li]) return TRPX_OK;
+        active[li] = false;
+        if (!cuda_ok(c, cudaStreamSynchronize(l.stream), "decode batch")) return TRPX_ERR_CUDA;
+        return status_of_device_word(l.h_small[1]);
+    };
+
+    for (size_t b = 0; b < n_batches && rc == TRPX_OK; ++b) {
+        const int li = (int)(b % N_LANES);
+        Lane& l = c->lanes[li];
+        rc = finish(li);
+        if (rc != TRPX_OK) break;
+        const size_t f0 = first_frame + b * fpb, nf = (b * fpb + fpb <= n_frames) ? fpb : n_frames - b * fpb;
+        const u64 slab0 = f0 ? ends[f0 - 1] : 0, slab1 = ends[f0 + nf - 1];
+        const size_t slab = (size_t)(slab1 - slab0);
+        if (slab1 > payload_bytes || slab1 <= slab0) { rc = TRPX_ERR_MALFORMED; break; }
+        if (!ensure(c, l.d_in, slab + 32) || !ensure(c, l.d_out, nf * frame_raw + 16) || !ensure(c, l.d_ends, nf * 8) ||
+            !ensure_host_ends(c, l, nf)) { rc = TRPX_ERR_NOMEM; break; }
+        for (size_t i = 0; i < nf; ++i) l.h_ends[i] = ends[f0 + i] - slab0;
+        DecPlan pl = dec_plan(out_dtype, slab, n_values, nf, block, l.d_out.p, c->seg_bytes, c->warm_bytes);
+        if (!pl.ok) { rc = TRPX_ERR_BAD_ARG; break; }
+        if (!ensure(c, l.dec_scratch, pl.scratch_bytes)) { rc = TRPX_ERR_NOMEM; break; }
+        cudaMemsetAsync((uint8_t*)l.d_in.p + (slab & ~(size_t)15), 0, 32, l.stream);   // defined bytes after the slab
+        if (!cuda_ok(c, cudaMemcpyAsync(l.d_in.p, payload + slab0, slab, cudaMemcpyHostToDevice, l.stream), "H2D payload") ||
+            !cuda_ok(c, cudaMemcpyAsync(l.d_ends.p, l.h_ends, nf * 8, cudaMemcpyHostToDevice, l.stream), "H2D ends")) {
+            rc = TRPX_ERR_CUDA;
+            break;
+        }
+        Launcher L = make_launcher(c, l.stream);
+        decode_async(L, l.d_in.p, slab, is_signed != 0, block, n_values, nf, (const u64*)l.d_ends.p, nullptr, l.d_out.p,
+                     out_dtype, l.d_small + 1, l.dec_scratch.p, pl, c->coop_grid);
+        if (!cuda_ok(c, L.err, "decode launch")) { rc = TRPX_ERR_CUDA; break; }
+        cudaMemcpyAsync((uint8_t*)out + b * fpb * frame_raw, l.d_out.p, nf * frame_raw, cudaMemcpyDeviceToHost, l.stream);
+        cudaMemcpyAsync(l.h_small, l.d_small, 8, cudaMemcpyDeviceToHost, l.stream);
+        active[li] = true;
+    }
+    for (int li = 0; li < N_LANES; ++li) {
+        int r = finish(li);
+        if (rc == TRPX_OK) rc = r;
+    }
+    if (rc != TRPX_OK)
+        for (int i = 0; i < N_LANES; ++i) cudaStreamSynchronize(c->lanes[i].stream);
+    return rc;
+}
+
+}  // extern "C"
