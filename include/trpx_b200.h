@@ -134,6 +134,12 @@ int trpx_ctx_lanes(const trpx_ctx* ctx);
 uint64_t trpx_ctx_launch_count(const trpx_ctx* ctx);
 /* Bytes of device scratch currently held by the context. */
 size_t trpx_ctx_scratch_bytes(const trpx_ctx* ctx);
+/* Profiling: when on, the *_device entry points drop a CUDA event on the caller's stream between
+ * their kernels.  Once that stream has drained, trpx_ctx_last_kernel_times() returns the device
+ * time (ms) of each kernel of the last call on `lane` (names[i]: static strings such as
+ * "terse_encode", "prolix_walk", "prolix_unpack"); the return value is the number of entries. */
+int trpx_ctx_set_profiling(trpx_ctx* ctx, int on);
+int trpx_ctx_last_kernel_times(trpx_ctx* ctx, int lane, const char** names, float* ms, int cap);
 
 #ifdef __cplusplus
 }

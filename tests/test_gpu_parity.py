@@ -1,0 +1,255 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (libtrpx_b200.so, include/trpx_b200.h),
+against the CPU oracle (== reference bytes, tests/test_oracle.py) and the committed golden vectors.
+Bit-exact: TERSE payload bytes, per-frame sizes and prolix_bits must equal the oracle's; PROLIX must
+return the original pixels (and the oracle's values for converting decodes).
+
+Needs a GPU; nothing here reads /root/reference."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import golden_util as G
+import orc
+import trpx_b200
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def codec():
+    c = trpx_b200.Codec(0)
+    yield c
+    c.close()
+
+
+def enc_check(codec, stack, block=12):
+    stack = np.ascontiguousarray(stack)
+    p, fb, pb = codec.encode(stack, block)
+    q, per, qb = orc.encode_stack(stack, block)
+    assert pb == qb
+    assert np.array_equal(fb, per)
+    assert p.size == q.size and np.array_equal(p, q)
+    return p, fb, pb
+
+
+def roundtrip(codec, stack, block=12, out_dtype=None, known_sizes=True):
+    stack = np.ascontiguousarray(stack)
+    F, N = stack.shape
+    p, fb, pb = enc_check(codec, stack, block)
+    od = stack.dtype if out_dtype is None else np.dtype(out_dtype)
+    sgn = stack.dtype.kind == "i"
+    got, fb2 = codec.decode(p, N, F, sgn, od, block, fb if known_sizes else None)
+    assert np.array_equal(fb2, fb)
+    ends = np.cumsum(fb).astype(np.int64)
+    if od == stack.dtype:
+        assert np.array_equal(got, stack)
+    else:
+        want = np.stack([orc.decode_frame(p[int(ends[f] - fb[f]):int(ends[f])], N, sgn, od, block)[0] for f in range(F)])
+        assert np.array_equal(got, want)
+
+
+# ---------------------------------------------------------------- golden vectors (reference-produced)
+@pytest.mark.parametrize("c", G.load("kat_small"), ids=lambda c: c["name"])
+def test_small_kats(codec, c):
+    a = G.small_input(c)
+    p, fb, pb = codec.encode(a[None, :], c["block"])
+    assert pb == c["prolix_bits"] and p.size == c["memory_size"]
+    if "payload_hex" in c:
+        assert p.tobytes().hex() == c["payload_hex"]
+    else:
+        assert hex(orc.fnv(p)) == c["fnv1a64"]
+    d, _ = codec.decode(p, a.size, 1, c["dtype"][0] == "i", a.dtype, c["block"])
+    assert np.array_equal(d[0], a)
+
+
+@pytest.mark.parametrize("c", G.load("kat_large"),
+                         ids=lambda c: "%s-%s-%d-%d" % (c["gen"], c["dtype"], c["seed"], c["n"]))
+def test_large_kats(codec, c):
+    a = G.large_input(c)
+    p, fb, pb = codec.encode(a[None, :])
+    assert (pb, p.size, hex(orc.fnv(p)), p[:8].tobytes().hex()) == \
+           (c["prolix_bits"], c["memory_size"], c["fnv1a64"], c["first8"])
+    d, _ = codec.decode(p, a.size, 1, c["dtype"][0] == "i", a.dtype)
+    assert np.array_equal(d[0], a)
+
+
+def test_stack_kat_is_concatenation(codec):
+    c = G.load("kat_files")[3]
+    st = np.stack([orc.kat_fill(orc.U16, c["n"], s) for s in c["seeds"]])
+    p, fb, pb = codec.encode(st)
+    assert hex(orc.fnv(p)) == c["payload_fnv1a64"] and int(fb.sum()) == p.size
+    assert orc.header(pb, False, 12, p.size, c["n"], [], c["frames"]).decode() == c["header"]
+    d, fb2 = codec.decode(p, c["n"], 2, False, np.uint16)          # frame sizes recovered from the stream
+    assert np.array_equal(d, st) and np.array_equal(fb2, fb)
+
+
+# ---------------------------------------------------------------- differential vs the oracle
+@pytest.mark.parametrize("dt", list(range(8)), ids=lambda d: str(np.dtype(orc.NP_OF[d])))
+def test_all_types_fast_path(codec, dt):
+    isz = orc.NP_OF[dt]().itemsize
+    n = 12 * 5000 + 8
+    while (n * isz) % 16:
+        n += 1
+    st = np.stack([orc.kat_fill(dt, n, 40 + f) for f in range(5)])
+    roundtrip(codec, st)
+
+
+def test_c2_shape_frames(codec):
+    """512x512 u16 Poisson + Bragg peaks (BASELINE configs[0]/[1] shape), 24 frames."""
+    st = np.stack([orc.synth_frame(orc.U16, 512, 512, 2.0, 200, 1000 + f) for f in range(24)])
+    roundtrip(codec, st)
+    roundtrip(codec, st[:3], known_sizes=False)
+
+
+def test_signed_dark_subtracted_frames(codec):
+    for dt in (orc.I16, orc.I32):
+        st = np.stack([orc.synth_frame(dt, 512, 512, 3.0, 0, 77 + f) for f in range(6)])
+        roundtrip(codec, st)
+
+
+def test_sparse_counting_frames(codec):
+    rng = np.random.default_rng(11)
+    for dt in (np.uint8, np.uint16):
+        st = (rng.random((3, 1536 * 1024)) < 0.02).astype(dt)
+        st[1] = 0
+        roundtrip(codec, st)
+    roundtrip(codec, np.zeros((7, 512 * 512), np.uint16))
+
+
+def test_tiny_and_ragged_frames(codec):
+    for n in (1, 3, 8, 11, 12, 13, 24, 100, 1000, 4097):
+        st = np.stack([orc.kat_fill(orc.U16, n, 7 + f) for f in range(9)])
+        roundtrip(codec, st)
+        roundtrip(codec, st, known_sizes=False)
+    roundtrip(codec, np.zeros((50, 8), np.uint16))
+    roundtrip(codec, np.zeros((1, 96), np.uint16))                 # 'ff 00': the extra byte rule
+
+
+@pytest.mark.parametrize("dt", [orc.U8, orc.U16, orc.I16, orc.U32, orc.I64])
+def test_generic_blocks(codec, dt):
+    rng = np.random.default_rng(5 + dt)
+    for block, n, frames in [(12, 1001, 3), (7, 500, 2), (1, 77, 2), (40, 999, 3), (5, 3, 4), (300, 5000, 2),
+                             (13, 100003, 2)]:
+        st = np.stack([orc.kat_fill(dt, n, int(rng.integers(1, 1 << 30))) for _ in range(frames)])
+        roundtrip(codec, st, block)
+
+
+def test_signed_extremes(codec):
+    a = np.array([-32768, 32767, -1, 0, 5, -5, 100, -100, 1, 2, 3, 4] * 4, np.int16)
+    roundtrip(codec, a[None, :])
+    roundtrip(codec, np.array([-2**63, 2**63 - 1, 0, -1] * 6, np.int64)[None, :])
+    roundtrip(codec, np.array([2**64 - 1, 0, 1, 2**63] * 6, np.uint64)[None, :])
+    roundtrip(codec, np.array([2**32 - 1] * 12, np.uint32)[None, :])   # s == W (reference decode fails, App. C5)
+
+
+@pytest.mark.parametrize("src,dst", [(np.uint16, np.uint8), (np.uint16, np.uint64), (np.uint16, np.int32),
+                                     (np.int16, np.int8), (np.int16, np.int64), (np.uint32, np.uint16),
+                                     (np.int32, np.int16), (np.uint8, np.uint32), (np.int64, np.int32)])
+def test_output_conversion_clamps_like_get_range(codec, src, dst):
+    rng = np.random.default_rng(3)
+    info = np.iinfo(src)
+    a = rng.integers(max(info.min, -70000), min(info.max, 70000), size=(2, 12 * 3000), endpoint=True).astype(src)
+    a[:, ::50] = info.max
+    if info.min < 0:
+        a[:, 7::50] = info.min + 1
+    roundtrip(codec, a, out_dtype=dst)
+
+
+def test_partial_decode_of_a_stack(codec):
+    st = np.stack([orc.kat_fill(orc.U16, 5000, 7 + f) for f in range(10)])
+    p, fb, pb = codec.encode(st)
+    d, _ = codec.decode(p, 5000, 10, False, np.uint16, frame_bytes=fb, first_frame=3, n_frames=4)
+    assert np.array_equal(d, st[3:7])
+    d, _ = codec.decode(p, 5000, 10, False, np.uint16, first_frame=9, n_frames=1)
+    assert np.array_equal(d, st[9:10])
+
+
+# ---------------------------------------------------------------- error behaviour
+def test_errors(codec):
+    st = np.stack([orc.kat_fill(orc.U16, 12 * 800, 3)])
+    with pytest.raises(trpx_b200.TrpxError) as e:
+        codec.encode(st, capacity=1024)
+    assert e.value.status == trpx_b200.ERR_CAPACITY
+    p, fb, pb = codec.encode(st)
+    with pytest.raises(trpx_b200.TrpxError) as e:
+        codec.decode(p[: p.size // 2], st.shape[1], 1, False, np.uint16)
+    assert e.value.status == trpx_b200.ERR_MALFORMED
+    with pytest.raises(trpx_b200.TrpxError) as e:                  # signed stream into unsigned output
+        codec.decode(p, st.shape[1], 1, True, np.uint16)
+    assert e.value.status == trpx_b200.ERR_BAD_ARG
+    # still usable afterwards
+    roundtrip(codec, st)
+
+
+# ---------------------------------------------------------------- device-pointer flavour + big shapes
+def test_device_flavour_large_stack_properties(codec):
+    """512x512 u16 x 2000 frames resident in HBM: round trip, frame-size bookkeeping, sample frames
+    byte-identical to the oracle, and the stack payload == concatenation of independently encoded
+    halves (frames are independent: the property multi-GPU sharding relies on)."""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda:0")
+    F, N = 2000, 512 * 512
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234)
+    px = torch.poisson(torch.full((F, N), 2.0, device=dev), generator=g).to(torch.int32)
+    hot = torch.randint(0, N, (F, 64), device=dev, generator=g)
+    px.scatter_(1, hot, torch.randint(20, 3000, (F, 64), device=dev, generator=g, dtype=torch.int32))
+    px = px.to(torch.uint16)
+    cap = trpx_b200.max_compressed_bytes(N, np.uint16, 12, F)
+    out = torch.empty(cap, dtype=torch.uint8, device=dev)
+    ends = torch.zeros(F, dtype=torch.int64, device=dev)
+    small = torch.zeros(4, dtype=torch.int32, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    codec.encode_device(px.data_ptr(), np.uint16, N, F, out.data_ptr(), cap, ends.data_ptr(), small.data_ptr(),
+                        small.data_ptr() + 4, s)
+    torch.cuda.synchronize()
+    assert int(small[1]) == 0
+    e = ends.cpu().numpy()
+    assert np.all(np.diff(e) > 0)
+    total = int(e[-1])
+    # sample frames against the oracle
+    host = out[:total].cpu().numpy()
+    for f in (0, 1, 999, 1999):
+        q, qb = orc.encode_frame(px[f].cpu().numpy())
+        lo = int(e[f - 1]) if f else 0
+        assert np.array_equal(host[lo:int(e[f])], q)
+        assert qb <= int(small[0])
+    # halves encode independently to the same bytes
+    out2 = torch.empty(cap, dtype=torch.uint8, device=dev)
+    ends2 = torch.zeros(F, dtype=torch.int64, device=dev)
+    h = F // 2
+    codec.encode_device(px[h:].data_ptr(), np.uint16, N, F - h, out2.data_ptr(), cap, ends2.data_ptr(),
+                        small.data_ptr() + 8, small.data_ptr() + 12, s)
+    torch.cuda.synchronize()
+    n2 = int(ends2[F - h - 1])
+    assert n2 == total - int(e[h - 1])
+    assert torch.equal(out2[:n2], out[int(e[h - 1]):total])
+    # decode on the device, known frame ends
+    back = torch.empty((F, N), dtype=torch.uint16, device=dev)
+    st = torch.zeros(1, dtype=torch.int32, device=dev)
+    codec.decode_device(out.data_ptr(), total, False, N, F, ends.data_ptr(), back.data_ptr(), np.uint16,
+                        st.data_ptr(), s)
+    torch.cuda.synchronize()
+    assert int(st[0]) == 0
+    assert torch.equal(back.view(torch.int16), px.view(torch.int16))
+
+
+@pytest.mark.parametrize("shape,dt,lam", [((4148, 4362), np.uint32, 0.5), ((5760, 4092), np.uint8, 0.02),
+                                          ((5760, 4092), np.uint16, 0.02)])
+def test_big_frames_roundtrip_and_oracle(codec, shape, dt, lam):
+    """Eiger2-16M-class u32 and cryo-EM movie frames (BASELINE configs[2], [3]): 2 frames each, oracle
+    bytes on the first, round trip on both."""
+    rng = np.random.default_rng(5)
+    n = shape[0] * shape[1]
+    st = rng.poisson(lam, size=(2, n)).astype(dt)
+    if dt == np.uint32:
+        st[0, rng.integers(0, n, 2000)] = rng.integers(1000, 1000000, 2000)
+        st[1, ::100003] = 0xFFFFFFFF                               # detector-gap pixels: s == 32
+    p, fb, pb = codec.encode(st)
+    q, qb = orc.encode_frame(st[0])
+    assert np.array_equal(p[: q.size], q) and int(fb[0]) == q.size
+    d, fb2 = codec.decode(p, n, 2, False, dt, frame_bytes=fb)
+    assert np.array_equal(d, st)
+    d1, _ = codec.decode(p[: int(fb[0])], n, 1, False, dt)
+    assert np.array_equal(d1[0], st[0])

@@ -21,7 +21,8 @@ OK, ERR_BAD_ARG, ERR_CAPACITY, ERR_CUDA, ERR_MALFORMED, ERR_NO_DEVICE, ERR_NOMEM
 EXPORTS = ["trpx_abi_version", "trpx_strerror", "trpx_dtype_size", "trpx_dtype_is_signed",
            "trpx_max_compressed_bytes", "trpx_ctx_create", "trpx_ctx_destroy", "trpx_ctx_device",
            "trpx_last_error", "trpx_ctx_lanes", "trpx_ctx_launch_count", "trpx_ctx_scratch_bytes",
-           "trpx_encode_host", "trpx_encode_device", "trpx_decode_host", "trpx_decode_device"]
+           "trpx_encode_host", "trpx_encode_device", "trpx_decode_host", "trpx_decode_device",
+           "trpx_ctx_set_profiling", "trpx_ctx_last_kernel_times"]
 
 
 class TrpxError(RuntimeError):
@@ -77,6 +78,10 @@ def lib(build_if_missing=True):
     L.trpx_ctx_launch_count.argtypes = [vp]
     L.trpx_ctx_scratch_bytes.restype = sz
     L.trpx_ctx_scratch_bytes.argtypes = [vp]
+    L.trpx_ctx_set_profiling.restype = i
+    L.trpx_ctx_set_profiling.argtypes = [vp, i]
+    L.trpx_ctx_last_kernel_times.restype = i
+    L.trpx_ctx_last_kernel_times.argtypes = [vp, i, C.POINTER(C.c_char_p), C.POINTER(C.c_float), i]
     L.trpx_encode_host.restype = i
     L.trpx_encode_host.argtypes = [vp, vp, i, sz, sz, u, vp, sz, vp, C.POINTER(sz), C.POINTER(u)]
     L.trpx_encode_device.restype = i
@@ -122,6 +127,16 @@ class Codec:
     @property
     def launches(self):
         return int(lib().trpx_ctx_launch_count(self._h))
+
+    def set_profiling(self, on=True):
+        self._check(lib().trpx_ctx_set_profiling(self._h, int(on)))
+
+    def last_kernel_times(self, lane=0):
+        """[(kernel name, device ms), ...] of the last *_device call on `lane` (stream must have drained)."""
+        names = (C.c_char_p * 32)()
+        ms = (C.c_float * 32)()
+        n = lib().trpx_ctx_last_kernel_times(self._h, lane, names, ms, 32)
+        return [(names[k].decode(), float(ms[k])) for k in range(n)]
 
     # ---- host-pointer flavour
     def encode(self, stack, block=12, capacity=None):

@@ -28,7 +28,12 @@ struct Launcher {
     u32 sm_count;               // SMs of the device (148 on B200)
     u64* launches;              // optional counter of kernels launched
     cudaError_t err;
-    void count() { if (launches) ++*launches; }
+    // optional profiling hook: called with a static name after every kernel (and once after the
+    // memsets that open a call), so the owner can drop an event on the stream between kernels
+    void (*mark_fn)(void* user, const char* name) = nullptr;
+    void* mark_user = nullptr;
+    void mark(const char* name) { if (mark_fn) mark_fn(mark_user, name); }
+    void count(const char* name) { if (launches) ++*launches; mark(name); }
 };
 
 // ---------------------------------------------------------------------------------- encode
@@ -92,7 +97,7 @@ inline void encode_launch_t(Launcher& L, const EncPlan& pl, EncParams p, u32 cta
     else
         L.err = launch(terse_encode_generic_kernel<T, GEN_NT>, (u32)grid, GEN_NT, pl.smem, L.stream, p,
                        pl.tile_blocks);
-    L.count();
+    L.count(pl.fast ? "terse_encode" : "terse_encode_generic");
 }
 
 template <typename T>
@@ -140,6 +145,7 @@ inline void encode_async(Launcher& L, int dtype, const void* d_pixels, u64 n_val
     cudaMemsetAsync(scratch, 0, pl.scratch_bytes, L.stream);
     cudaMemsetAsync(d_prolix_bits, 0, sizeof(u32), L.stream);
     cudaMemsetAsync(d_status, 0, sizeof(u32), L.stream);
+    L.mark("memset");
     switch (dtype) {
     case DT_U8: encode_launch_t<uint8_t>(L, pl, p, ctas_per_sm); break;
     case DT_U16: encode_launch_t<uint16_t>(L, pl, p, ctas_per_sm); break;
@@ -209,7 +215,7 @@ inline void unpack_launch_t(Launcher& L, const DecPlan& pl, const DecParams& p)
         L.err = launch(prolix_unpack_kernel<O, SGN, true>, (u32)pl.n_tiles, DEC_NT, pl.smem_unpack, L.stream, p);
     else
         L.err = launch(prolix_unpack_kernel<O, SGN, false>, (u32)pl.n_tiles, DEC_NT, pl.smem_unpack, L.stream, p);
-    L.count();
+    L.count("prolix_unpack");
 }
 template <bool SGN>
 inline void unpack_launch(Launcher& L, int out_dtype, const DecPlan& pl, const DecParams& p)
@@ -262,6 +268,7 @@ inline void decode_async(Launcher& L, const void* d_payload, u64 payload_bytes, 
     p.status = d_status;
     cudaMemsetAsync(d_status, 0, sizeof(u32), L.stream);
     cudaMemsetAsync(sc + pl.off_zero_begin, 0, pl.scratch_bytes - pl.off_zero_begin, L.stream);
+    L.mark("memset");
     if (d_frame_ends == nullptr) {
         u64* fe = d_frame_ends_out ? d_frame_ends_out : (u64*)(sc + pl.off_frame_ends);
         if (n_frames == 1) {
@@ -270,23 +277,23 @@ inline void decode_async(Launcher& L, const void* d_payload, u64 payload_bytes, 
         } else {
             L.err = launch(prolix_find_frames_kernel, 1u, 32u, 0, L.stream, p, fe);
         }
-        L.count();
+        L.count("prolix_find_frames");
         if (L.err != cudaSuccess) return;
         d_frame_ends = fe;
     }
     p.frame_ends = d_frame_ends;
     L.err = launch(prolix_segments_kernel<SEGTAB_NT>, 1u, (u32)SEGTAB_NT, 0, L.stream, p);
-    L.count();
+    L.count("prolix_segments");
     if (L.err != cudaSuccess) return;
     const u32 walk_grid = (u32)div_up(pl.max_segs, WALK_NT);
     L.err = launch(prolix_walk_kernel<WALK_NT>, walk_grid, (u32)WALK_NT, 0, L.stream, p);
-    L.count();
+    L.count("prolix_walk");
     if (L.err != cudaSuccess) return;
     L.err = launch_coop(prolix_resolve_kernel<RESOLVE_NT>, coop_grid, (u32)RESOLVE_NT, 0, L.stream, p);
-    L.count();
+    L.count("prolix_resolve");
     if (L.err != cudaSuccess) return;
     L.err = launch(prolix_emit_kernel<WALK_NT>, walk_grid, (u32)WALK_NT, 0, L.stream, p);
-    L.count();
+    L.count("prolix_emit");
     if (L.err != cudaSuccess) return;
     if (is_signed) unpack_launch<true>(L, out_dtype, pl, p);
     else unpack_launch<false>(L, out_dtype, pl, p);

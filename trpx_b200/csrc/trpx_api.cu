@@ -34,6 +34,11 @@ struct Lane {
     u32* h_small = nullptr;            // pinned mirror
     u64* h_ends = nullptr;             // pinned copy of frame ends
     size_t h_ends_cap = 0;
+    // profiling (trpx_ctx_set_profiling): events dropped between the kernels of the last call
+    cudaStream_t prof_stream = nullptr;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<const char*> ev_names;
+    size_t ev_used = 0;
 };
 
 }  // namespace
@@ -48,6 +53,7 @@ struct trpx_ctx {
     u32 seg_bytes = 16384, warm_bytes = 8192;
     size_t batch_bytes = 256u << 20;   // raw pixel bytes per pipeline batch of the host flavours
     u32 coop_grid = 0;
+    bool profiling = false;
 };
 
 namespace {
@@ -100,13 +106,32 @@ u32 enc_ctas_per_sm(trpx_ctx* c, int dtype, const EncPlan& pl)
     return (u32)n;
 }
 
-Launcher make_launcher(trpx_ctx* c, cudaStream_t s)
+void prof_mark(void* user, const char* name)
+{
+    Lane* l = (Lane*)user;
+    if (l->ev_used == l->ev_pool.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        l->ev_pool.push_back(e);
+        l->ev_names.push_back(name);
+    }
+    l->ev_names[l->ev_used] = name;
+    cudaEventRecord(l->ev_pool[l->ev_used++], l->prof_stream);
+}
+
+Launcher make_launcher(trpx_ctx* c, cudaStream_t s, Lane* lane = nullptr)
 {
     Launcher L;
     L.stream = s;
     L.sm_count = (u32)c->sm_count;
     L.launches = &c->launches;
     L.err = cudaSuccess;
+    if (c->profiling && lane) {
+        lane->prof_stream = s;
+        lane->ev_used = 0;
+        L.mark_fn = prof_mark;
+        L.mark_user = lane;
+    }
     return L;
 }
 
@@ -195,6 +220,7 @@ void trpx_ctx_destroy(trpx_ctx* c)
         if (l.d_small) cudaFree(l.d_small);
         if (l.h_small) cudaFreeHost(l.h_small);
         if (l.h_ends) cudaFreeHost(l.h_ends);
+        for (cudaEvent_t e : l.ev_pool) cudaEventDestroy(e);
     }
     delete c;
 }
@@ -214,6 +240,28 @@ size_t trpx_ctx_scratch_bytes(const trpx_ctx* c)
     return t;
 }
 
+int trpx_ctx_set_profiling(trpx_ctx* c, int on)
+{
+    if (!c) return TRPX_ERR_BAD_ARG;
+    c->profiling = on != 0;
+    return TRPX_OK;
+}
+
+int trpx_ctx_last_kernel_times(trpx_ctx* c, int lane, const char** names, float* ms, int cap)
+{
+    if (!c || lane < 0 || lane >= N_LANES) return 0;
+    Lane& l = c->lanes[lane];
+    int n = 0;
+    for (size_t i = 1; i < l.ev_used && n < cap; ++i) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, l.ev_pool[i - 1], l.ev_pool[i]) != cudaSuccess) { cudaGetLastError(); break; }
+        if (names) names[n] = l.ev_names[i];
+        if (ms) ms[n] = t;
+        ++n;
+    }
+    return n;
+}
+
 // ------------------------------------------------------------------------------ TERSE, device pointers
 int trpx_encode_device(trpx_ctx* c, int lane, const void* d_pixels, int dtype, size_t n_values,
                        size_t n_frames, unsigned block, uint8_t* d_out, size_t out_capacity,
@@ -229,7 +277,7 @@ int trpx_encode_device(trpx_ctx* c, int lane, const void* d_pixels, int dtype, s
     if (!pl.ok) { c->last_error = "unsupported geometry (block too large or too many tiles)"; return TRPX_ERR_BAD_ARG; }
     Lane& l = c->lanes[lane];
     if (!ensure(c, l.enc_scratch, pl.scratch_bytes)) return TRPX_ERR_NOMEM;
-    Launcher L = make_launcher(c, (cudaStream_t)stream);
+    Launcher L = make_launcher(c, (cudaStream_t)stream, &l);
     encode_async(L, dtype, d_pixels, n_values, n_frames, block, d_out, out_capacity, (u64*)d_frame_ends,
                  d_prolix_bits, d_status, l.enc_scratch.p, pl, enc_ctas_per_sm(c, dtype, pl));
     if (!cuda_ok(c, L.err, "encode launch")) return TRPX_ERR_CUDA;
@@ -252,7 +300,7 @@ int trpx_decode_device(trpx_ctx* c, int lane, const uint8_t* d_payload, size_t p
     if (!pl.ok) return TRPX_ERR_BAD_ARG;
     Lane& l = c->lanes[lane];
     if (!ensure(c, l.dec_scratch, pl.scratch_bytes)) return TRPX_ERR_NOMEM;
-    Launcher L = make_launcher(c, (cudaStream_t)stream);
+    Launcher L = make_launcher(c, (cudaStream_t)stream, &l);
     decode_async(L, d_payload, payload_bytes, is_signed != 0, block, n_values, n_frames, (const u64*)d_frame_ends,
                  (u64*)d_frame_ends_out, d_out, out_dtype, d_status, l.dec_scratch.p, pl, c->coop_grid);
     if (!cuda_ok(c, L.err, "decode launch")) return TRPX_ERR_CUDA;
@@ -383,7 +431,7 @@ int trpx_decode_host(trpx_ctx* c, const uint8_t* payload, size_t payload_bytes, 
         cudaMemsetAsync(l.d_small, 0, 8, l.stream);
         Launcher L = make_launcher(c, l.stream);
         L.err = launch(prolix_find_frames_kernel, 1u, 32u, 0, l.stream, p, (u64*)l.d_ends.p);
-        L.count();
+        L.count("prolix_find_frames");
         if (!cuda_ok(c, L.err, "find frames launch")) return TRPX_ERR_CUDA;
         cudaMemcpyAsync(ends.data(), l.d_ends.p, total_frames * 8, cudaMemcpyDeviceToHost, l.stream);
         cudaMemcpyAsync(l.h_small, l.d_small, 8, cudaMemcpyDeviceToHost, l.stream);
