@@ -39,6 +39,7 @@ struct State {
     ucontext_t sched;
     int current = -1;
     uint32_t bar_count = 0, bar_gen = 0;
+    uint32_t nbar_count[16] = {0}, nbar_gen[16] = {0};   // named barriers (bar.sync id, n)
     std::vector<uint32_t> wbar_count, wbar_gen;
     std::vector<uint64_t> xch;            // 32 slots per warp
     unsigned char* smem = nullptr;
@@ -65,6 +66,14 @@ inline void sync_block()
     uint32_t gen = s.bar_gen;
     if (++s.bar_count == cur().block_dim) { s.bar_count = 0; ++s.bar_gen; progress(); }
     else while (s.bar_gen == gen) yield();
+}
+
+inline void bar_sync(uint32_t id, uint32_t n)
+{
+    State& s = S();
+    uint32_t gen = s.nbar_gen[id & 15];
+    if (++s.nbar_count[id & 15] == n) { s.nbar_count[id & 15] = 0; ++s.nbar_gen[id & 15]; progress(); }
+    else while (s.nbar_gen[id & 15] == gen) yield();
 }
 
 inline void sync_warp()
@@ -126,7 +135,7 @@ inline uint32_t warp_reduce(uint32_t v, int op)
 }
 
 // mbarrier emulation in the barrier's own 8 bytes
-struct MBar { uint8_t expected, arrived, phase, pad; int32_t tx; };
+struct MBar { uint16_t expected, arrived; int32_t tx : 31; uint32_t phase : 1; };
 static_assert(sizeof(MBar) == 8, "emulated mbarrier must fit the 8-byte hardware object");
 inline void mbar_check(MBar* b)
 {
@@ -136,7 +145,13 @@ inline void mbar_init(unsigned long long* bar, uint32_t count)
 {
     MBar* b = (MBar*)bar;
     memset(b, 0, sizeof(MBar));
-    b->expected = (uint8_t)count;
+    b->expected = (uint16_t)count;
+}
+inline void mbar_arrive(unsigned long long* bar)
+{
+    MBar* b = (MBar*)bar;
+    b->arrived++;
+    mbar_check(b);
 }
 inline void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes)
 {
@@ -190,6 +205,7 @@ inline void run_grid(uint32_t grid, uint32_t block, size_t smem_bytes, const std
     uint32_t nw = (block + 31) / 32;
     for (uint32_t b = 0; b < grid; ++b) {
         s.bar_count = 0; s.bar_gen = 0;
+        memset(s.nbar_count, 0, sizeof(s.nbar_count)); memset(s.nbar_gen, 0, sizeof(s.nbar_gen));
         s.wbar_count.assign(nw, 0); s.wbar_gen.assign(nw, 0);
         s.xch.assign((size_t)nw * 32, 0);
         memset(smem_buf, 0xA5, smem_bytes);              // uninitialised shared memory is garbage

@@ -89,3 +89,12 @@ def test_capacity_error():
     st = np.stack([orc.kat_fill(orc.U16, 12 * 800, 3)])
     p, ends, pb, status, fast = emu_lib.encode(st, cap=1024)
     assert status == 2
+
+
+def test_groups_of_more_than_64_tiles():
+    """Frames longer than one look-back group (64 tiles) and a group that ends mid-frame."""
+    rng = np.random.default_rng(9)
+    n = 3072 * 67 + 100                                  # u32 tile = 3072 values -> 68 tiles, 2 groups per frame
+    st = (rng.random((3, n)) < 0.05).astype(np.uint32) * rng.integers(1, 5000, size=(3, n), dtype=np.uint32)
+    assert check(st) is True
+    assert check(st, incl_stride=3) is True

@@ -40,9 +40,10 @@ struct Launcher {
 struct EncPlan {
     bool fast;                  // block == 12 and 16-byte aligned frames: TMA-staged kernel
     u32 tile_blocks;
-    u64 nblocks, tiles_per_frame, n_tiles;
+    u64 nblocks, tiles_per_frame, n_tiles, groups_per_frame, n_groups;
+    u32 threads;                // threads per CTA
     size_t smem;                // dynamic shared memory per CTA
-    size_t scratch_bytes;       // ticket + descriptors + tails
+    size_t scratch_bytes;       // ticket + tile descriptors + tails + group descriptors
     bool ok;
 };
 
@@ -56,7 +57,9 @@ inline EncPlan enc_plan_t(const void* d_pixels, u64 n_values, u64 n_frames, u32 
     if (pl.fast) {
         pl.tile_blocks = EncGeom<T, ENC_NT>::TILE_BLOCKS;
         pl.smem = EncGeom<T, ENC_NT>::SMEM_BYTES;
+        pl.threads = EncGeom<T, ENC_NT>::THREADS;
     } else {
+        pl.threads = GEN_NT;
         const u64 maxbits = 12 + (u64)block * (Pix<T>::W + (Pix<T>::SGN ? 1 : 0));
         const u64 cap_bits = (u64)GenGeom<T, GEN_NT>::STG_WORDS_MAX * 32;
         u64 tb = cap_bits / maxbits;
@@ -68,7 +71,9 @@ inline EncPlan enc_plan_t(const void* d_pixels, u64 n_values, u64 n_frames, u32 
     pl.tiles_per_frame = div_up(pl.nblocks, pl.tile_blocks);
     pl.n_tiles = pl.tiles_per_frame * n_frames;
     if (pl.n_tiles >= (1ull << 31)) pl.ok = false;
-    pl.scratch_bytes = 64 + (size_t)pl.n_tiles * 16;
+    pl.groups_per_frame = div_up(pl.tiles_per_frame, GROUP);
+    pl.n_groups = pl.groups_per_frame * n_frames;
+    pl.scratch_bytes = 64 + (size_t)pl.n_tiles * 16 + (size_t)pl.n_groups * 8;
     return pl;
 }
 
@@ -93,7 +98,7 @@ inline void encode_launch_t(Launcher& L, const EncPlan& pl, EncParams p, u32 cta
     if (grid > pl.n_tiles) grid = pl.n_tiles;
     if (grid == 0) return;
     if (pl.fast)
-        L.err = launch(terse_encode_kernel<T, ENC_NT>, (u32)grid, ENC_NT, pl.smem, L.stream, p);
+        L.err = launch(terse_encode_kernel<T, ENC_NT>, (u32)grid, pl.threads, pl.smem, L.stream, p);
     else
         L.err = launch(terse_encode_generic_kernel<T, GEN_NT>, (u32)grid, GEN_NT, pl.smem, L.stream, p,
                        pl.tile_blocks);
@@ -138,9 +143,11 @@ inline void encode_async(Launcher& L, int dtype, const void* d_pixels, u64 n_val
     p.frame_ends = d_frame_ends;
     p.prolix_bits = d_prolix_bits;
     p.status = d_status;
+    p.groups_per_frame = pl.groups_per_frame;
     p.ticket = (u32*)scratch;
-    p.desc = (u64*)((unsigned char*)scratch + 64);
-    p.tails = p.desc + pl.n_tiles;
+    p.tdesc = (u64*)((unsigned char*)scratch + 64);
+    p.tails = p.tdesc + pl.n_tiles;
+    p.gdesc = p.tails + pl.n_tiles;
     p.dbg_incl_stride = dbg_incl_stride;
     cudaMemsetAsync(scratch, 0, pl.scratch_bytes, L.stream);
     cudaMemsetAsync(d_prolix_bits, 0, sizeof(u32), L.stream);

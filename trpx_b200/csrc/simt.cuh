@@ -41,6 +41,9 @@ TRPX_DEVICE u32 nthreads() { return blockDim.x; }
 TRPX_DEVICE u32 nblocks() { return gridDim.x; }
 TRPX_DEVICE void sync_block() { __syncthreads(); }
 TRPX_DEVICE void sync_warp() { __syncwarp(); }
+// named barrier `id` (1..15) over `n` threads (a multiple of 32): lets the worker warps of a
+// warp-specialised CTA synchronise among themselves without the resolver warps
+TRPX_DEVICE void bar_sync(u32 id, u32 n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 TRPX_DEVICE void spin_hint() { __nanosleep(32); }
 TRPX_DEVICE void trap() { __trap(); }
 
@@ -110,6 +113,10 @@ TRPX_DEVICE void mbar_arrive_expect_tx(u64* bar, u32 bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
                  : "memory");
+}
+TRPX_DEVICE void mbar_arrive(u64* bar)    // release.cta: the arriving thread's earlier shared-memory writes are visible to waiters
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
 TRPX_DEVICE bool mbar_try_wait(u64* bar, u32 parity)
 {
@@ -193,6 +200,7 @@ inline u32 nthreads() { return ::emu::cur().block_dim; }
 inline u32 nblocks() { return ::emu::cur().grid_dim; }
 inline void sync_block() { ::emu::sync_block(); }
 inline void sync_warp() { ::emu::sync_warp(); }
+inline void bar_sync(u32 id, u32 n) { ::emu::bar_sync(id, n); }
 inline void spin_hint() { ::emu::yield(); }
 inline void trap() { ::emu::trap(); }
 
@@ -260,6 +268,7 @@ inline void st_stream(uint4* p, uint4 v) { *p = v; }
 inline void mbar_init(u64* bar, u32 count) { ::emu::mbar_init(bar, count); }
 inline void mbar_init_fence() {}
 inline void mbar_arrive_expect_tx(u64* bar, u32 bytes) { ::emu::mbar_arrive_expect_tx(bar, bytes); }
+inline void mbar_arrive(u64* bar) { ::emu::mbar_arrive(bar); }
 inline void mbar_wait(u64* bar, u32 parity) { ::emu::mbar_wait(bar, parity); }
 inline void bulk_g2s(void* d, const void* s, u32 bytes, u64* bar) { ::emu::bulk_g2s(d, s, bytes, bar); }
 inline void bulk_s2g(void* d, const void* s, u32 bytes) { ::emu::bulk_s2g(d, s, bytes); }

@@ -61,13 +61,15 @@ struct EncParams {
     u64 nblocks;            // blocks per frame
     u64 tiles_per_frame;
     u64 n_tiles;
+    u64 groups_per_frame;   // ceil(tiles_per_frame / GROUP)
     u32* out_words;         // payload, 4-byte aligned
     u64 out_capacity;       // bytes
     u64* frame_ends;        // [n_frames] end byte offset of each frame
     u32* prolix_bits;       // [1], zeroed
     u32* status;            // [1], zeroed
-    u64* desc;              // [n_tiles] zeroed
-    u64* tails;             // [n_tiles] zeroed
+    u64* tdesc;             // [n_tiles] zeroed: level-1 descriptors (bits of a tile)
+    u64* gdesc;             // [n_groups] zeroed: level-2 descriptors (groups of <= 64 tiles of one frame)
+    u64* tails;             // [n_tiles] zeroed: boundary-word hand-off
     u32* ticket;            // [1] zeroed
     u32 dbg_incl_stride;    // tests only: publish INCL for every k-th tile only (0 = always)
 };
@@ -236,7 +238,7 @@ TRPX_DEVICE void pack_block12(BitSink& sk, const u32* w, u32 s, u32 cnt)
 // ------------------------------------------------------------------ K3: block-wide exclusive scan
 // len -> tile-relative bit offset; warp shuffles + one shared round.  Contains ONE sync_block().
 template <int NT>
-TRPX_DEVICE void scan_lengths(u32 len, u32* sm_warp_tot, u32& off, u32& tile_bits)
+TRPX_DEVICE void scan_lengths(u32 len, u32* sm_warp_tot, u32& off, u32& tile_bits, u32 named_bar = 0)
 {
     const u32 t = tid(), lane = t & 31, warp = t >> 5;
     u32 incl = len;
@@ -246,7 +248,7 @@ TRPX_DEVICE void scan_lengths(u32 len, u32* sm_warp_tot, u32& off, u32& tile_bit
         if (lane >= (u32)d) incl += v;
     }
     if (lane == 31) sm_warp_tot[warp] = incl;
-    sync_block();
+    if (named_bar) bar_sync(named_bar, NT); else sync_block();
     u32 base = 0, total = 0;
 #pragma unroll
     for (int i = 0; i < NT / 32; ++i) {
@@ -300,8 +302,35 @@ TRPX_DEVICE void merge_and_flush(BitSink& sk, u32 end_off)
     }
 }
 
-// Decoupled look-back over the frame-aware position maps; executed by one whole warp.
-// Returns the stream position (bits) at which `tile` starts.
+// ------------------------------------------------------------------ two-level look-back
+// A flat decoupled look-back tops out near (32 descriptors / L2 round trip) ~ 32 tiles per
+// microsecond -- far below the ~300 tiles/us this kernel has to sustain with 12 KB tiles.  So the chain
+// has two levels.  Tiles are grouped into GROUPs of <= 64 consecutive tiles of ONE frame:
+//   level 1  tdesc[tile] = VALID | bits.  A tile's offset inside its group is the sum of its <= 63
+//            predecessors' bits: one coalesced read of the group's descriptors, no chain at all.
+//   level 2  gdesc[group] = status | ends | value, the frame-aware look-back described at the top of
+//            this file, but over groups (64x fewer links); the group's last tile publishes it.
+constexpr u32 GROUP = 64;
+constexpr u64 TD_VALID = 1ull << 63;
+
+struct TileGeom { u64 frame, tif, group, gfirst_tile; u32 j, m; bool ends, gends; };
+TRPX_DEVICE TileGeom tile_geom(const EncParams& p, u64 tile)
+{
+    TileGeom g;
+    g.frame = tile / p.tiles_per_frame;
+    g.tif = tile % p.tiles_per_frame;
+    const u64 gif = g.tif / GROUP;                         // group inside the frame
+    g.group = g.frame * p.groups_per_frame + gif;
+    g.j = (u32)(g.tif % GROUP);
+    const u64 left = p.tiles_per_frame - gif * GROUP;
+    g.m = left < GROUP ? (u32)left : GROUP;
+    g.gfirst_tile = tile - g.j;
+    g.ends = g.tif + 1 == p.tiles_per_frame;
+    g.gends = gif + 1 == p.groups_per_frame;
+    return g;
+}
+
+// Level 2: stream position (bits) at which `group` starts; executed by one whole warp.
 TRPX_DEVICE u64 lookback_start(const u64* desc, u64 tile)
 {
     if (tile == 0) return 0;
@@ -323,7 +352,7 @@ TRPX_DEVICE u64 lookback_start(const u64* desc, u64 tile)
             if (spins > (1u << 24)) trap();               // never hang the device
             spin_hint();
         }
-        for (u32 l = 0; l < first_incl; ++l) {            // nearest tile first: g <- g o f_l
+        for (u32 l = 0; l < first_incl; ++l) {            // nearest first: g <- g o f_l
             const u64 dl = shfl(d, (int)l);
             g = fn_after_tile(g, (dl & ENDS_BIT) != 0, dl & VAL_MASK);
         }
@@ -332,45 +361,104 @@ TRPX_DEVICE u64 lookback_start(const u64* desc, u64 tile)
     }
 }
 
-// Shared by both encoder kernels: after the tile's bits sit in `stg` (tile-relative), find the
-// tile's stream position, publish it, and store the words this tile owns, shifted into place.
-//   bc[0] = P0, bc[1] = tail_in        (written by thread 0, read by all after the sync)
+// Both levels; executed by one whole warp (all lanes return the tile's start position P0).
+TRPX_DEVICE u64 tile_start(const EncParams& p, u64 tile, const TileGeom& g, u32 tile_bits)
+{
+    const u32 lane = tid() & 31;
+    if (lane == 0) st_relaxed(&p.tdesc[tile], TD_VALID | (u64)tile_bits);
+    // level 1: bits of the tiles before me in my group
+    const bool need0 = lane < g.j, need1 = lane + 32 < g.j;
+    u64 d0 = 0, d1 = 0;
+    for (u32 spins = 0;; ++spins) {
+        if (need0 && !(d0 & TD_VALID)) d0 = ld_relaxed(&p.tdesc[g.gfirst_tile + lane]);
+        if (need1 && !(d1 & TD_VALID)) d1 = ld_relaxed(&p.tdesc[g.gfirst_tile + 32 + lane]);
+        const bool ok = (!need0 || (d0 & TD_VALID)) && (!need1 || (d1 & TD_VALID));
+        if (all_lanes(ok)) break;
+        if (spins > (1u << 24)) trap();
+        spin_hint();
+    }
+    const u32 before = warp_add((need0 ? (u32)d0 : 0u) + (need1 ? (u32)d1 : 0u));
+    // level 2: the group's start; its last tile also publishes the group's aggregate and end position
+    const bool last = g.j + 1 == g.m;
+    const u64 gbits = (u64)before + tile_bits;
+    if (last && lane == 0)
+        st_relaxed(&p.gdesc[g.group], (ST_AGG << ST_SHIFT) | (g.gends ? ENDS_BIT : 0) | gbits);
+    const u64 Pg = lookback_start(p.gdesc, g.group);
+    if (last && lane == 0 && (p.dbg_incl_stride == 0 || g.group % p.dbg_incl_stride == 0))
+        st_relaxed(&p.gdesc[g.group], (ST_INCL << ST_SHIFT) | (g.gends ? align_frame(Pg + gbits) : Pg + gbits));
+    return Pg + before;
+}
+
+// word i of a tile's output window: staging words shifted left by the start position's bit offset
+TRPX_DEVICE u32 window_word(const u32* stg, u32 nstg, u32 i, u32 sh)
+{
+    const u32 lo = (i >= 1 && i - 1 < nstg) ? stg[i - 1] : 0u;
+    const u32 hi = i < nstg ? stg[i] : 0u;
+    return funnel_l(lo, hi, sh);
+}
+
+// The word two neighbouring tiles share is stored by the LATER tile; the earlier one hands its bits of
+// that word over through tails[].  One thread.  Returns the predecessor's bits of our first word.
+TRPX_DEVICE u32 tail_handoff(const EncParams& p, u64 tile, const u32* stg, u32 tile_bits, u64 P0, u64 Pn, u32& tout)
+{
+    const u32 nstg = (tile_bits + 31) >> 5;
+    const u32 k = (u32)((Pn >> 5) - (P0 >> 5));            // complete words this tile owns
+    const u32 sh = (u32)(P0 & 31);
+    // Our bits of the word the NEXT tile starts in.  When we own a complete word (k >= 1) they do not
+    // depend on our predecessor: publish before waiting, so the hand-off never chains across tiles.
+    tout = window_word(stg, nstg, k, sh);
+    if (k >= 1) st_relaxed(&p.tails[tile], TAIL_VALID | (u64)tout);
+    u64 tin = 0;
+    if (sh != 0) {                                         // the word we start in is ours to store
+        for (u32 spins = 0;; ++spins) {
+            tin = ld_relaxed(&p.tails[tile - 1]);
+            if (tin & TAIL_VALID) break;
+            if (spins > (1u << 24)) trap();
+            spin_hint();
+        }
+    }
+    tin &= 0xffffffffull;
+    if (k == 0) { tout |= (u32)tin; st_relaxed(&p.tails[tile], TAIL_VALID | (u64)tout); }
+    return (u32)tin;
+}
+
+// Store the words a tile owns, shifted into place; `rank` of `nthr` cooperating threads.
+TRPX_DEVICE void store_tile(const EncParams& p, u64 tile, const TileGeom& g, const u32* stg, u32 tile_bits,
+                            u64 P0, u64 Pn, u32 tail_in, u32 tout, u32 rank, u32 nthr)
+{
+    const u32 nstg = (tile_bits + 31) >> 5;
+    const u64 W0 = P0 >> 5, Wn = Pn >> 5;
+    const u32 sh = (u32)(P0 & 31);
+    const u32 k = (u32)(Wn - W0);
+    const bool fits = ((Pn + 7) >> 3) <= p.out_capacity;
+    if (fits) {
+        for (u32 i = rank; i < k; i += nthr)
+            st_stream(&p.out_words[W0 + i], window_word(stg, nstg, i, sh) | (i == 0 ? tail_in : 0u));
+    } else if (rank == 0) {
+        atomic_max(p.status, 2u);                          // TRPX_ERR_CAPACITY
+    }
+    if (rank == 0) {
+        if (g.ends) p.frame_ends[g.frame] = Pn >> 3;
+        if (tile + 1 == p.n_tiles && fits) {               // nobody follows: store the final bytes
+            unsigned char* ob = (unsigned char*)p.out_words;
+            for (u32 b = 0; b < (u32)((Pn >> 3) & 3); ++b) ob[Wn * 4 + b] = (unsigned char)(tout >> (8 * b));
+        }
+    }
+}
+
+// In-line variant (generic kernel): warp 0 resolves, then the whole CTA stores.
+//   bc[0] = P0, bc[1] = tail_in, bc[2] = tail_out   (written by thread 0, read by all after the sync)
 template <int NT>
-TRPX_DEVICE void resolve_and_store(const EncParams& p, u64 tile, bool ends, u32 tile_bits,
-                                   const u32* stg, u64* bc)
+TRPX_DEVICE void resolve_and_store(const EncParams& p, u64 tile, u32 tile_bits, const u32* stg, u64* bc)
 {
     const u32 t = tid();
-    const u32 nstg = (tile_bits + 31) >> 5;
-    // word i of this tile's output window (without the predecessor's bits of word 0)
-    auto word_at = [&](u32 i, u32 sh) -> u32 {
-        u32 lo = (i >= 1 && i - 1 < nstg) ? stg[i - 1] : 0u;
-        u32 hi = i < nstg ? stg[i] : 0u;
-        return funnel_l(lo, hi, sh);
-    };
+    const TileGeom g = tile_geom(p, tile);
     if (t < 32) {
-        const u64 P0 = lookback_start(p.desc, tile);
+        const u64 P0 = tile_start(p, tile, g, tile_bits);
         if (t == 0) {
-            const u64 Pn = ends ? align_frame(P0 + tile_bits) : P0 + tile_bits;
-            if (p.dbg_incl_stride == 0 || tile % p.dbg_incl_stride == 0)
-                st_relaxed(&p.desc[tile], (ST_INCL << ST_SHIFT) | Pn);
-            const u32 k = (u32)((Pn >> 5) - (P0 >> 5));
-            const u32 sh = (u32)(P0 & 31);
-            // Our bits of the word the NEXT tile starts in.  When we own a complete word (k >= 1)
-            // they do not depend on our predecessor: publish before waiting, so the hand-off never
-            // forms a chain across tiles.
-            u32 tout = word_at(k, sh);
-            if (k >= 1) st_relaxed(&p.tails[tile], TAIL_VALID | (u64)tout);
-            u64 tin = 0;
-            if (sh != 0) {                                 // the word we start in is ours to store:
-                for (u32 spins = 0;; ++spins) {            // fetch the predecessor's bits of it
-                    tin = ld_relaxed(&p.tails[tile - 1]);
-                    if (tin & TAIL_VALID) break;
-                    if (spins > (1u << 24)) trap();
-                    spin_hint();
-                }
-            }
-            tin &= 0xffffffffull;
-            if (k == 0) { tout |= (u32)tin; st_relaxed(&p.tails[tile], TAIL_VALID | (u64)tout); }
+            const u64 Pn = g.ends ? align_frame(P0 + tile_bits) : P0 + tile_bits;
+            u32 tout;
+            const u32 tin = tail_handoff(p, tile, stg, tile_bits, P0, Pn, tout);
             bc[0] = P0;
             bc[1] = tin;
             bc[2] = tout;
@@ -378,36 +466,22 @@ TRPX_DEVICE void resolve_and_store(const EncParams& p, u64 tile, bool ends, u32 
     }
     sync_block();
     const u64 P0 = bc[0];
-    const u32 tail_in = (u32)bc[1];
-    const u64 Pn = ends ? align_frame(P0 + tile_bits) : P0 + tile_bits;
-    const u64 W0 = P0 >> 5, Wn = Pn >> 5;
-    const u32 sh = (u32)(P0 & 31);
-    const u32 k = (u32)(Wn - W0);                          // complete words this tile owns
-    const bool fits = ((Pn + 7) >> 3) <= p.out_capacity;
-    if (fits) {
-        for (u32 i = t; i < k; i += NT) st_stream(&p.out_words[W0 + i], word_at(i, sh) | (i == 0 ? tail_in : 0u));
-    } else if (t == 0) {
-        atomic_max(p.status, 2u);                          // TRPX_ERR_CAPACITY
-    }
-    if (t == 0) {
-        if (ends) p.frame_ends[tile / p.tiles_per_frame] = Pn >> 3;
-        if (tile + 1 == p.n_tiles && fits) {               // nobody follows: store the final bytes
-            const u32 tout = (u32)bc[2];
-            unsigned char* ob = (unsigned char*)p.out_words;
-            for (u32 b = 0; b < (u32)((Pn >> 3) & 3); ++b) ob[Wn * 4 + b] = (unsigned char)(tout >> (8 * b));
-        }
-    }
+    const u64 Pn = g.ends ? align_frame(P0 + tile_bits) : P0 + tile_bits;
+    store_tile(p, tile, g, stg, tile_bits, P0, Pn, (u32)bc[1], (u32)bc[2], t, NT);
 }
 
 // ------------------------------------------------------------------ shared-memory layout
-constexpr int ENC_STAGES = 2;
-constexpr int SM_BARS = 0;          // ENC_STAGES mbarriers, 16 bytes apart
+constexpr int ENC_STAGES = 2;       // TMA pixel stages
+constexpr int ENC_SLOTS = 2;        // packed-bit staging slots == resolver warps
+constexpr int SM_BARS = 0;          // mbarriers, 8 bytes each: full[STAGES], ready[SLOTS], packed[SLOTS], free[SLOTS]
 constexpr int SM_TICKETS = 64;      // ENC_STAGES u32
 constexpr int SM_WARP_TOT = 128;    // 32 u32
 constexpr int SM_WARP_LAST = 256;   // 32 u32
-constexpr int SM_BCAST = 384;       // 4 u64
-constexpr int SM_MAX = 448;         // u32 running max width
+constexpr int SM_BCAST = 384;       // 4 u64 (generic kernel)
+constexpr int SM_MAX = 416;         // u32 running max width
+constexpr int SM_MAIL = 448;        // ENC_SLOTS x {u64 tile, u32 bits, u32 pad}
 constexpr int SM_HEADER = 512;
+constexpr u64 TILE_END = ~0ull;
 
 template <typename T, int NT>
 struct EncGeom {
@@ -415,30 +489,82 @@ struct EncGeom {
     static constexpr int TILE_BYTES = NT * P::UNIT_BYTES;
     static constexpr int TILE_BLOCKS = NT * P::BPU;
     static constexpr int STAGE_BYTES = ((P::UNIT_BYTES + TILE_BYTES + 127) / 128) * 128;   // halo + tile
-    static constexpr int STG_WORDS = (TILE_BLOCKS * P::MAXBITS + 31) / 32 + 4;
-    static constexpr int SMEM_BYTES = SM_HEADER + ENC_STAGES * STAGE_BYTES + STG_WORDS * 4;
+    static constexpr int STG_WORDS = ((TILE_BLOCKS * P::MAXBITS + 31) / 32 + 4 + 3) / 4 * 4;
+    static constexpr int SMEM_BYTES = SM_HEADER + ENC_STAGES * STAGE_BYTES + ENC_SLOTS * STG_WORDS * 4;
+    static constexpr int THREADS = NT + 32 * ENC_SLOTS;    // worker warps + resolver warps
 };
 
 // ------------------------------------------------------------------ fast kernel: block == 12, 16-byte aligned frames
+// Warp-specialised persistent CTA.
+//   workers (NT threads)   wait for a TMA-staged tile, keep their 48 bytes in registers, compute widths /
+//                          headers / lengths, scan, pack into a staging slot in tile-relative coordinates.
+//                          They never wait for global memory: their only blocking points are the TMA
+//                          full-barrier (prefetched two tiles ahead) and a free staging slot.
+//   resolvers (1 warp per staging slot, alternating tiles)
+//                          publish the tile's bit count, find its stream position with the two-level
+//                          look-back, exchange the boundary word with the neighbour tile and store the
+//                          staged words, shifted into place, with coalesced streaming stores.
 template <typename T, int NT>
-TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) terse_encode_kernel(EncParams p)
+TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_SLOTS, 3) terse_encode_kernel(EncParams p)
 {
     typedef Pix<T> P;
     typedef EncGeom<T, NT> G;
     TRPX_DYN_SMEM(sm);
     u64* bars = (u64*)(sm + SM_BARS);
+    u64* bar_full = bars;
+    u64* bar_ready = bars + ENC_STAGES;
+    u64* bar_packed = bar_ready + ENC_SLOTS;
+    u64* bar_free = bar_packed + ENC_SLOTS;
     u32* tickets = (u32*)(sm + SM_TICKETS);
     u32* sm_warp_tot = (u32*)(sm + SM_WARP_TOT);
     u32* sm_warp_last = (u32*)(sm + SM_WARP_LAST);
-    u64* bc = (u64*)(sm + SM_BCAST);
     u32* sm_max = (u32*)(sm + SM_MAX);
+    volatile u64* mail_tile = (volatile u64*)(sm + SM_MAIL);            // [slot * 2]
+    volatile u32* mail_bits = (volatile u32*)(sm + SM_MAIL + 8);        // [slot * 4]
     unsigned char* stages = sm + SM_HEADER;
-    u32* stg = (u32*)(stages + ENC_STAGES * G::STAGE_BYTES);
+    u32* stg_base = (u32*)(stages + ENC_STAGES * G::STAGE_BYTES);
 
     const u32 t = tid(), lane = t & 31, warp = t >> 5;
     const u64 frame_bytes = p.n_values * P::SZ;
 
-    // thread 0 is the TMA producer: take the next ticket, start that tile's bulk copy
+    if (t == 0) {
+        for (int s = 0; s < ENC_STAGES; ++s) mbar_init(&bar_full[s], 1);
+        for (int s = 0; s < ENC_SLOTS; ++s) {
+            mbar_init(&bar_ready[s], 1);
+            mbar_init(&bar_packed[s], NT);
+            mbar_init(&bar_free[s], 1);
+        }
+        mbar_init_fence();
+        *sm_max = 0;
+    }
+    sync_block();
+
+    if (t >= (u32)NT) {
+        // ================================================================ resolver warp `slot`
+        const u32 slot = (t - NT) >> 5;
+        const u32* stg = stg_base + slot * G::STG_WORDS;
+        for (u32 use = 0;; ++use) {
+            mbar_wait(&bar_ready[slot], use & 1);
+            const u64 tile = mail_tile[slot * 2];
+            const u32 tile_bits = mail_bits[slot * 4];
+            if (tile == TILE_END) break;
+            const TileGeom g = tile_geom(p, tile);
+            const u64 P0 = tile_start(p, tile, g, tile_bits);
+            const u64 Pn = g.ends ? align_frame(P0 + tile_bits) : P0 + tile_bits;
+            mbar_wait(&bar_packed[slot], use & 1);         // the workers' staging stores are visible now
+            u32 tin = 0, tout = 0;
+            if (lane == 0) tin = tail_handoff(p, tile, stg, tile_bits, P0, Pn, tout);
+            tin = shfl(tin, 0);
+            tout = shfl(tout, 0);
+            store_tile(p, tile, g, stg, tile_bits, P0, Pn, tin, tout, lane, 32);
+            sync_warp();
+            if (lane == 0) mbar_arrive(&bar_free[slot]);   // slot (and its mailbox) may be reused
+        }
+        return;
+    }
+
+    // ==================================================================== worker warps
+    // thread 0 is also the TMA producer: take the next ticket, start that tile's bulk copy
     auto issue = [&](int s) {
         const u32 tk = atomic_add(p.ticket, 1u);
         tickets[s] = tk;
@@ -450,33 +576,27 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) terse_encode_kernel(EncParams p)
             const unsigned char* src = (const unsigned char*)p.pixels + f * frame_bytes + tile_off;
             unsigned char* dst = stages + s * G::STAGE_BYTES + P::UNIT_BYTES;
             if (tif > 0) { src -= P::UNIT_BYTES; dst -= P::UNIT_BYTES; bytes += P::UNIT_BYTES; }   // halo: previous block
-            mbar_arrive_expect_tx(&bars[2 * s], (u32)bytes);
-            bulk_g2s(dst, src, (u32)bytes, &bars[2 * s]);
+            mbar_arrive_expect_tx(&bar_full[s], (u32)bytes);
+            bulk_g2s(dst, src, (u32)bytes, &bar_full[s]);
         }
     };
-
-    if (t == 0) {
-        for (int s = 0; s < ENC_STAGES; ++s) mbar_init(&bars[2 * s], 1);
-        mbar_init_fence();
-        *sm_max = 0;
-    }
-    sync_block();
     if (t == 0)
         for (int s = 0; s < ENC_STAGES; ++s) issue(s);
-    sync_block();
+    bar_sync(1, NT);
 
     u32 my_max = 0;
-    for (u32 it = 0;; ++it) {
+    u32 it = 0;
+    for (;; ++it) {
         const int s = (int)(it % ENC_STAGES);
+        const u32 slot = it % ENC_SLOTS, use = it / ENC_SLOTS;
         const u64 tile = tickets[s];
         if (tile >= p.n_tiles) break;
         const u64 tif = tile % p.tiles_per_frame;
-        const bool ends = tif + 1 == p.tiles_per_frame;
         const u64 first_val = tif * (u64)(G::TILE_BLOCKS * 12);
         u64 tile_vals = p.n_values - first_val;
         if (tile_vals > (u64)(G::TILE_BLOCKS * 12)) tile_vals = G::TILE_BLOCKS * 12;
 
-        mbar_wait(&bars[2 * s], (it / ENC_STAGES) & 1);
+        mbar_wait(&bar_full[s], (it / ENC_STAGES) & 1);
 
         // ---- this thread's unit -> registers
         u32 w[P::UW];
@@ -519,7 +639,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) terse_encode_kernel(EncParams p)
             prev0 = block_width12<T>(h);
         }
         if (lane == 31) sm_warp_last[warp] = sb[P::BPU - 1];
-        sync_block();                                      // A: stage `s` is free, warp_last visible
+        bar_sync(1, NT);                                   // A: stage `s` is free, warp_last visible
         if (t == 0) issue(s);
 
         // ---- K2: headers and lengths
@@ -536,13 +656,18 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) terse_encode_kernel(EncParams p)
             }
         }
 
-        // ---- K3: offsets inside the tile; publish the tile's bit count for the look-back
+        // ---- K3: offsets inside the tile; hand the tile's bit count to the resolver
         u32 off, tile_bits;
-        scan_lengths<NT>(len, sm_warp_tot, off, tile_bits);    // sync B inside
-        if (t == 0)
-            st_relaxed(&p.desc[tile], (ST_AGG << ST_SHIFT) | (ends ? ENDS_BIT : 0) | (u64)tile_bits);
+        scan_lengths<NT>(len, sm_warp_tot, off, tile_bits, 1);   // bar B inside
+        mbar_wait(&bar_free[slot], (use + 1) & 1);         // the slot's previous tile has been stored
+        if (t == 0) {
+            mail_tile[slot * 2] = tile;
+            mail_bits[slot * 4] = tile_bits;
+            mbar_arrive(&bar_ready[slot]);
+        }
+        u32* stg = stg_base + slot * G::STG_WORDS;
         zero_boundary_words<NT>(stg, off, tile_bits);
-        sync_block();                                      // C
+        bar_sync(1, NT);                                   // C
 
         // ---- K4: pack into tile-relative staging
         BitSink sk;
@@ -554,15 +679,23 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) terse_encode_kernel(EncParams p)
                 pack_block12<T>(sk, &w[b * P::BW], sb[b], cnt[b]);
             }
         merge_and_flush(sk, off + len);
-        sync_block();                                      // D: staging complete
-
-        resolve_and_store<NT>(p, tile, ends, tile_bits, stg, bc);
-        // no barrier needed here: every shared word reused by the next iteration is rewritten only
-        // after one of its barriers A..D, which no thread passes before all finished this store.
+        mbar_arrive(&bar_packed[slot]);                    // D: all NT workers arrive -> staging complete
+        // Shared scratch reused by the next iteration is rewritten only after one of its barriers
+        // A..C, which no worker passes before all have finished reading this iteration's values.
+    }
+    // tell both resolvers that there is nothing more (in ticket order, after their slots drained)
+    if (t == 0) {
+        for (u32 k = 0; k < (u32)ENC_SLOTS; ++k) {
+            const u32 slot = (it + k) % ENC_SLOTS, use = (it + k) / ENC_SLOTS;
+            mbar_wait(&bar_free[slot], (use + 1) & 1);
+            mail_tile[slot * 2] = TILE_END;
+            mail_bits[slot * 4] = 0;
+            mbar_arrive(&bar_ready[slot]);
+        }
     }
     my_max = warp_max(my_max);
     if (lane == 0 && my_max) atomic_max(sm_max, my_max);
-    sync_block();
+    bar_sync(1, NT);
     if (t == 0 && *sm_max) atomic_max(p.prolix_bits, *sm_max);
 }
 
@@ -631,8 +764,6 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) terse_encode_generic_kernel(EncParams
         if (have) { block_header(s, prev, hv, hl); len = hl + s * cnt; }
         u32 off, tile_bits;
         scan_lengths<NT>(len, sm_warp_tot, off, tile_bits);
-        if (t == 0)
-            st_relaxed(&p.desc[tile], (ST_AGG << ST_SHIFT) | (ends ? ENDS_BIT : 0) | (u64)tile_bits);
         zero_boundary_words<NT>(stg, off, tile_bits);
         sync_block();
         BitSink sk;
@@ -644,7 +775,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) terse_encode_generic_kernel(EncParams
         }
         merge_and_flush(sk, off + len);
         sync_block();
-        resolve_and_store<NT>(p, tile, ends, tile_bits, stg, bc);
+        resolve_and_store<NT>(p, tile, tile_bits, stg, bc);
     }
     my_max = warp_max(my_max);
     if (lane == 0 && my_max) atomic_max(sm_max, my_max);

@@ -100,7 +100,7 @@ u32 enc_ctas_per_sm(trpx_ctx* c, int dtype, const EncPlan& pl)
     int n = 0;
     const void* k = enc_kernel(dtype, pl.fast);
     if (pl.smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, pl.fast ? ENC_NT : GEN_NT, pl.smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, (int)pl.threads, pl.smem);
     if (e != cudaSuccess || n < 1) { cudaGetLastError(); n = 1; }
     (void)c;
     return (u32)n;
