@@ -285,7 +285,7 @@ def run_ours(a):
 
     def decode(nbytes):
         codec.decode_device(payload.data_ptr(), nbytes, False, N_VALUES, F, ends.data_ptr(), back.data_ptr(),
-                            np.uint16, small.data_ptr() + 8, stream)
+                            np.uint16, small.data_ptr() + 8, stream, lane=1)
 
     # ---- untimed: first pass, correctness of the full-size workload (round trip on the device)
     encode()
@@ -319,7 +319,7 @@ def run_ours(a):
             # per-kernel device times come from events the library drops between its kernels; reading
             # them needs a drained stream, so this costs one host sync per step (outside the kernels)
             torch.cuda.synchronize()
-            for name, ms in codec.last_kernel_times(0):
+            for name, ms in codec.last_kernel_times(0) + codec.last_kernel_times(1):
                 ktimes.setdefault(name, []).append(ms)
     torch.cuda.synchronize()
     launches = codec.launches - l0

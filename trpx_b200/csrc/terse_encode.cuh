@@ -331,18 +331,23 @@ TRPX_DEVICE TileGeom tile_geom(const EncParams& p, u64 tile)
 }
 
 // Level 2: stream position (bits) at which `group` starts; executed by one whole warp.
-TRPX_DEVICE u64 lookback_start(const u64* desc, u64 tile)
+TRPX_DEVICE u64 lookback_first_round(const u64* desc, u64 tile)   // issue round 0's load early
+{
+    const i64 idx = (i64)tile - 1 - (i64)(tid() & 31);
+    return idx >= 0 ? ld_relaxed(&desc[idx]) : (ST_INCL << ST_SHIFT);
+}
+TRPX_DEVICE u64 lookback_start(const u64* desc, u64 tile, u64 d_first)
 {
     if (tile == 0) return 0;
     const u32 lane = tid() & 31;
     FrameFn g = fn_identity();
     i64 base = (i64)tile - 1;
-    for (;;) {
+    for (u32 round = 0;; ++round) {
         const i64 idx = base - (i64)lane;
-        u64 d;
+        u64 d = d_first;
         u32 first_incl;
         for (u32 spins = 0;; ++spins) {
-            d = idx >= 0 ? ld_relaxed(&desc[idx]) : (ST_INCL << ST_SHIFT);   // "tile -1": position 0
+            if (round | spins) d = idx >= 0 ? ld_relaxed(&desc[idx]) : (ST_INCL << ST_SHIFT);   // "tile -1": position 0
             const u32 st = (u32)(d >> ST_SHIFT);
             const u32 incl_mask = ballot(st == ST_INCL);
             const u32 inval_mask = ballot(st == ST_INVALID);
@@ -362,10 +367,11 @@ TRPX_DEVICE u64 lookback_start(const u64* desc, u64 tile)
 }
 
 // Both levels; executed by one whole warp (all lanes return the tile's start position P0).
-TRPX_DEVICE u64 tile_start(const EncParams& p, u64 tile, const TileGeom& g, u32 tile_bits)
+TRPX_DEVICE u64 tile_start(const EncParams& p, u64 tile, const TileGeom& g, u32 tile_bits, bool publish)
 {
     const u32 lane = tid() & 31;
-    if (lane == 0) st_relaxed(&p.tdesc[tile], TD_VALID | (u64)tile_bits);
+    if (publish && lane == 0) st_relaxed(&p.tdesc[tile], TD_VALID | (u64)tile_bits);
+    const u64 dg = lookback_first_round(p.gdesc, g.group);  // in flight together with the level-1 loads
     // level 1: bits of the tiles before me in my group
     const bool need0 = lane < g.j, need1 = lane + 32 < g.j;
     u64 d0 = 0, d1 = 0;
@@ -383,7 +389,7 @@ TRPX_DEVICE u64 tile_start(const EncParams& p, u64 tile, const TileGeom& g, u32 
     const u64 gbits = (u64)before + tile_bits;
     if (last && lane == 0)
         st_relaxed(&p.gdesc[g.group], (ST_AGG << ST_SHIFT) | (g.gends ? ENDS_BIT : 0) | gbits);
-    const u64 Pg = lookback_start(p.gdesc, g.group);
+    const u64 Pg = lookback_start(p.gdesc, g.group, dg);
     if (last && lane == 0 && (p.dbg_incl_stride == 0 || g.group % p.dbg_incl_stride == 0))
         st_relaxed(&p.gdesc[g.group], (ST_INCL << ST_SHIFT) | (g.gends ? align_frame(Pg + gbits) : Pg + gbits));
     return Pg + before;
@@ -454,7 +460,7 @@ TRPX_DEVICE void resolve_and_store(const EncParams& p, u64 tile, u32 tile_bits, 
     const u32 t = tid();
     const TileGeom g = tile_geom(p, tile);
     if (t < 32) {
-        const u64 P0 = tile_start(p, tile, g, tile_bits);
+        const u64 P0 = tile_start(p, tile, g, tile_bits, true);
         if (t == 0) {
             const u64 Pn = g.ends ? align_frame(P0 + tile_bits) : P0 + tile_bits;
             u32 tout;
@@ -473,13 +479,13 @@ TRPX_DEVICE void resolve_and_store(const EncParams& p, u64 tile, u32 tile_bits, 
 // ------------------------------------------------------------------ shared-memory layout
 constexpr int ENC_STAGES = 2;       // TMA pixel stages
 constexpr int ENC_SLOTS = 2;        // packed-bit staging slots == resolver warps
-constexpr int SM_BARS = 0;          // mbarriers, 8 bytes each: full[STAGES], ready[SLOTS], packed[SLOTS], free[SLOTS]
+constexpr int SM_BARS = 0;          // mbarriers, 8 bytes each: full[STAGES], ready[SLOTS], packed[SLOTS], resolved[SLOTS]
 constexpr int SM_TICKETS = 64;      // ENC_STAGES u32
 constexpr int SM_WARP_TOT = 128;    // 32 u32
 constexpr int SM_WARP_LAST = 256;   // 32 u32
 constexpr int SM_BCAST = 384;       // 4 u64 (generic kernel)
 constexpr int SM_MAX = 416;         // u32 running max width
-constexpr int SM_MAIL = 448;        // ENC_SLOTS x {u64 tile, u32 bits, u32 pad}
+constexpr int SM_MAIL = 448;        // ENC_SLOTS x {u64 tile, u64 P0, u32 bits, u32 tail_in, u32 tail_out, u32 pad} (32 bytes each)
 constexpr int SM_HEADER = 512;
 constexpr u64 TILE_END = ~0ull;
 
@@ -497,13 +503,15 @@ struct EncGeom {
 // ------------------------------------------------------------------ fast kernel: block == 12, 16-byte aligned frames
 // Warp-specialised persistent CTA.
 //   workers (NT threads)   wait for a TMA-staged tile, keep their 48 bytes in registers, compute widths /
-//                          headers / lengths, scan, pack into a staging slot in tile-relative coordinates.
-//                          They never wait for global memory: their only blocking points are the TMA
-//                          full-barrier (prefetched two tiles ahead) and a free staging slot.
+//                          headers / lengths, scan, publish the tile's bit count, pack into a staging slot
+//                          in tile-relative coordinates.  The slot's PREVIOUS tile (two iterations ago) is
+//                          stored first -- shifted into place, coalesced streaming stores -- by which time
+//                          its stream position has long been resolved, so workers never wait for global
+//                          memory round trips; their blocking points are the TMA full-barrier (prefetched
+//                          two tiles ahead) and that resolution.
 //   resolvers (1 warp per staging slot, alternating tiles)
-//                          publish the tile's bit count, find its stream position with the two-level
-//                          look-back, exchange the boundary word with the neighbour tile and store the
-//                          staged words, shifted into place, with coalesced streaming stores.
+//                          find the tile's stream position with the two-level look-back and exchange the
+//                          boundary word with the neighbour tile: pure latency, off the workers' path.
 template <typename T, int NT>
 TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_SLOTS, 3) terse_encode_kernel(EncParams p)
 {
@@ -514,13 +522,13 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_SLOTS, 3) terse_encode_kernel(
     u64* bar_full = bars;
     u64* bar_ready = bars + ENC_STAGES;
     u64* bar_packed = bar_ready + ENC_SLOTS;
-    u64* bar_free = bar_packed + ENC_SLOTS;
+    u64* bar_resolved = bar_packed + ENC_SLOTS;
     u32* tickets = (u32*)(sm + SM_TICKETS);
     u32* sm_warp_tot = (u32*)(sm + SM_WARP_TOT);
     u32* sm_warp_last = (u32*)(sm + SM_WARP_LAST);
     u32* sm_max = (u32*)(sm + SM_MAX);
-    volatile u64* mail_tile = (volatile u64*)(sm + SM_MAIL);            // [slot * 2]
-    volatile u32* mail_bits = (volatile u32*)(sm + SM_MAIL + 8);        // [slot * 4]
+    volatile u64* mail64 = (volatile u64*)(sm + SM_MAIL);               // [slot * 4 + {0: tile, 1: P0}]
+    volatile u32* mail32 = (volatile u32*)(sm + SM_MAIL);               // [slot * 8 + {4: bits, 5: tail_in, 6: tail_out}]
     unsigned char* stages = sm + SM_HEADER;
     u32* stg_base = (u32*)(stages + ENC_STAGES * G::STAGE_BYTES);
 
@@ -532,7 +540,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_SLOTS, 3) terse_encode_kernel(
         for (int s = 0; s < ENC_SLOTS; ++s) {
             mbar_init(&bar_ready[s], 1);
             mbar_init(&bar_packed[s], NT);
-            mbar_init(&bar_free[s], 1);
+            mbar_init(&bar_resolved[s], 1);
         }
         mbar_init_fence();
         *sm_max = 0;
@@ -545,20 +553,22 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_SLOTS, 3) terse_encode_kernel(
         const u32* stg = stg_base + slot * G::STG_WORDS;
         for (u32 use = 0;; ++use) {
             mbar_wait(&bar_ready[slot], use & 1);
-            const u64 tile = mail_tile[slot * 2];
-            const u32 tile_bits = mail_bits[slot * 4];
+            const u64 tile = mail64[slot * 4];
+            const u32 tile_bits = mail32[slot * 8 + 4];
             if (tile == TILE_END) break;
             const TileGeom g = tile_geom(p, tile);
-            const u64 P0 = tile_start(p, tile, g, tile_bits);
+            const u64 P0 = tile_start(p, tile, g, tile_bits, false);
             const u64 Pn = g.ends ? align_frame(P0 + tile_bits) : P0 + tile_bits;
             mbar_wait(&bar_packed[slot], use & 1);         // the workers' staging stores are visible now
-            u32 tin = 0, tout = 0;
-            if (lane == 0) tin = tail_handoff(p, tile, stg, tile_bits, P0, Pn, tout);
-            tin = shfl(tin, 0);
-            tout = shfl(tout, 0);
-            store_tile(p, tile, g, stg, tile_bits, P0, Pn, tin, tout, lane, 32);
+            if (lane == 0) {
+                u32 tout;
+                const u32 tin = tail_handoff(p, tile, stg, tile_bits, P0, Pn, tout);
+                mail64[slot * 4 + 1] = P0;
+                mail32[slot * 8 + 5] = tin;
+                mail32[slot * 8 + 6] = tout;
+                mbar_arrive(&bar_resolved[slot]);
+            }
             sync_warp();
-            if (lane == 0) mbar_arrive(&bar_free[slot]);   // slot (and its mailbox) may be reused
         }
         return;
     }
@@ -579,6 +589,16 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_SLOTS, 3) terse_encode_kernel(
             mbar_arrive_expect_tx(&bar_full[s], (u32)bytes);
             bulk_g2s(dst, src, (u32)bytes, &bar_full[s]);
         }
+    };
+    // store the tile that occupies staging slot `slot` (its `use`-th tile), once resolved
+    auto store_slot = [&](u32 slot, u32 use) {
+        mbar_wait(&bar_resolved[slot], use & 1);
+        const u64 ptile = mail64[slot * 4];
+        const u64 P0 = mail64[slot * 4 + 1];
+        const u32 pbits = mail32[slot * 8 + 4];
+        const TileGeom g = tile_geom(p, ptile);
+        const u64 Pn = g.ends ? align_frame(P0 + pbits) : P0 + pbits;
+        store_tile(p, ptile, g, stg_base + slot * G::STG_WORDS, pbits, P0, Pn, mail32[slot * 8 + 5], mail32[slot * 8 + 6], t, NT);
     };
     if (t == 0)
         for (int s = 0; s < ENC_STAGES; ++s) issue(s);
@@ -656,16 +676,21 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_SLOTS, 3) terse_encode_kernel(
             }
         }
 
-        // ---- K3: offsets inside the tile; hand the tile's bit count to the resolver
+        // ---- K3: offsets inside the tile
         u32 off, tile_bits;
         scan_lengths<NT>(len, sm_warp_tot, off, tile_bits, 1);   // bar B inside
-        mbar_wait(&bar_free[slot], (use + 1) & 1);         // the slot's previous tile has been stored
-        if (t == 0) {
-            mail_tile[slot * 2] = tile;
-            mail_bits[slot * 4] = tile_bits;
-            mbar_arrive(&bar_ready[slot]);
-        }
+        // publish the tile's bit count at once: other tiles' look-backs must never wait for our resolver
+        if (t == 0) st_relaxed(&p.tdesc[tile], TD_VALID | (u64)tile_bits);
+
+        // ---- the slot's previous tile goes out (resolved two tile-times ago), then the slot is ours
         u32* stg = stg_base + slot * G::STG_WORDS;
+        if (use > 0) store_slot(slot, use - 1);
+        bar_sync(1, NT);                                   // E: slot and mailbox are free
+        if (t == 0) {
+            mail64[slot * 4] = tile;
+            mail32[slot * 8 + 4] = tile_bits;
+            mbar_arrive(&bar_ready[slot]);                 // the resolver may start its look-back
+        }
         zero_boundary_words<NT>(stg, off, tile_bits);
         bar_sync(1, NT);                                   // C
 
@@ -683,13 +708,16 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_SLOTS, 3) terse_encode_kernel(
         // Shared scratch reused by the next iteration is rewritten only after one of its barriers
         // A..C, which no worker passes before all have finished reading this iteration's values.
     }
-    // tell both resolvers that there is nothing more (in ticket order, after their slots drained)
+    // drain: the last tiles still sitting in the staging slots, oldest first
+    for (u32 k = (it < (u32)ENC_SLOTS ? it : (u32)ENC_SLOTS); k >= 1; --k) {
+        const u32 j = it - k;
+        store_slot(j % ENC_SLOTS, j / ENC_SLOTS);
+    }
+    bar_sync(1, NT);
+    // tell both resolvers that there is nothing more
     if (t == 0) {
-        for (u32 k = 0; k < (u32)ENC_SLOTS; ++k) {
-            const u32 slot = (it + k) % ENC_SLOTS, use = (it + k) / ENC_SLOTS;
-            mbar_wait(&bar_free[slot], (use + 1) & 1);
-            mail_tile[slot * 2] = TILE_END;
-            mail_bits[slot * 4] = 0;
+        for (u32 slot = 0; slot < (u32)ENC_SLOTS; ++slot) {
+            mail64[slot * 4] = TILE_END;
             mbar_arrive(&bar_ready[slot]);
         }
     }
