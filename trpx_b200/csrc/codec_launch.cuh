@@ -66,7 +66,7 @@ inline EncPlan enc_plan_t(const void* d_pixels, u64 n_values, u64 n_frames, u32 
         if (tb > (u64)GEN_NT) tb = GEN_NT;
         if (tb == 0) { pl.ok = false; tb = 1; }            // block too large for one CTA's staging
         pl.tile_blocks = (u32)tb;
-        pl.smem = SM_HEADER + (size_t)((tb * maxbits + 31) / 32 + 4) * 4;
+        pl.smem = SM_HEADER + (size_t)((tb * maxbits + 31) / 32 + 12) * 4;
     }
     pl.tiles_per_frame = div_up(pl.nblocks, pl.tile_blocks);
     pl.n_tiles = pl.tiles_per_frame * n_frames;

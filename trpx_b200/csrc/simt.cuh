@@ -137,6 +137,14 @@ TRPX_DEVICE void mbar_wait(u64* bar, u32 parity)
         if (spins > (1u << 26)) trap();
 }
 
+TRPX_DEVICE void mbar_wait_sleep(u64* bar, u32 parity)   // for long, uncritical waits
+{
+    for (u32 spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+        if (spins > (1u << 24)) trap();
+        __nanosleep(64);
+    }
+}
+
 // ---- TMA bulk copies (1-D): SASS UBLKCP ----
 // global -> shared, completion counted in bytes on `bar`; src/dst 16-byte aligned, bytes % 16 == 0
 TRPX_DEVICE void bulk_g2s(void* smem_dst, const void* gsrc, u32 bytes, u64* bar)
@@ -270,6 +278,7 @@ inline void mbar_init_fence() {}
 inline void mbar_arrive_expect_tx(u64* bar, u32 bytes) { ::emu::mbar_arrive_expect_tx(bar, bytes); }
 inline void mbar_arrive(u64* bar) { ::emu::mbar_arrive(bar); }
 inline void mbar_wait(u64* bar, u32 parity) { ::emu::mbar_wait(bar, parity); }
+inline void mbar_wait_sleep(u64* bar, u32 parity) { ::emu::mbar_wait(bar, parity); }
 inline void bulk_g2s(void* d, const void* s, u32 bytes, u64* bar) { ::emu::bulk_g2s(d, s, bytes, bar); }
 inline void bulk_s2g(void* d, const void* s, u32 bytes) { ::emu::bulk_s2g(d, s, bytes); }
 inline void bulk_commit() {}

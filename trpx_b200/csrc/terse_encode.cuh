@@ -156,6 +156,26 @@ struct BitSink {
             nb -= 32;
         }
     }
+    // n in [0, 64], v < 2^n.  Same contract as put(); up to two words complete per call.  Written
+    // without data-dependent branches so that lanes with different widths stay converged.
+    TRPX_DEVICE void put64(u64 v, u32 n)
+    {
+        const u32 ov = funnel_l((u32)(v >> 32), 0u, nb);       // bits pushed past bit 63 (nb < 32)
+        acc |= v << nb;
+        nb += n;
+        const u32 c = nb >> 5;                                  // complete words: 0, 1 or 2
+        const u32 a0 = (u32)acc, a1 = (u32)(acc >> 32);
+        if (c >= 1) {
+            if (!crossed) head = a0; else stg[w] = a0;
+            if (c >= 2) stg[w + 1] = a1;
+            crossed = true;
+        }
+        const u32 n0 = c == 0 ? a0 : (c == 1 ? a1 : ov);
+        const u32 n1 = c == 0 ? a1 : (c == 1 ? ov : 0u);
+        acc = (u64)n0 | ((u64)n1 << 32);
+        w += c;
+        nb &= 31;
+    }
     TRPX_DEVICE void put_wide(u64 v, u32 s)   // low s bits of the sign-extended value, s in [1, 65]
     {
         u32 n0 = s < 32 ? s : 32;
@@ -193,22 +213,16 @@ TRPX_DEVICE void pack_block12(BitSink& sk, const u32* w, u32 s, u32 cnt)
     if (s == 0) return;
     if (cnt == 12) {
         if (P::SZ == 2 && s <= 16) {
-            const u32 m = P::SGN ? ((1u << s) - 1) * 0x00010001u : 0xffffffffu;   // s<=16: per-half mask
-            if (s <= 8) {
+            // two 16-bit halves -> one field of 2s bits with a single multiply-add:
+            // lo + hi*2^16 + hi*(2^s - 2^16) == lo + hi*2^s; two such pairs -> one 64-bit put
+            const u32 m = ((1u << s) - 1) * 0x00010001u;             // s <= 16: per-half mask (signed only)
+            const u32 K = (1u << s) - 65536u;
+            const u32 s2 = 2 * s;
 #pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    u32 x0 = w[2 * q] & m, x1 = w[2 * q + 1] & m;
-                    u32 p0 = (x0 & 0xffffu) | ((x0 >> 16) << s);
-                    u32 p1 = (x1 & 0xffffu) | ((x1 >> 16) << s);
-                    sk.put(p0 | (p1 << (2 * s)), 4 * s);
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < 6; ++q) {
-                    u32 x = w[q] & m;
-                    if (s == 16) sk.put(x, 32);
-                    else sk.put((x & 0xffffu) | ((x >> 16) << s), 2 * s);
-                }
+            for (int q = 0; q < 3; ++q) {
+                const u32 x0 = P::SGN ? (w[2 * q] & m) : w[2 * q], x1 = P::SGN ? (w[2 * q + 1] & m) : w[2 * q + 1];
+                const u32 p0 = x0 + (x0 >> 16) * K, p1 = x1 + (x1 >> 16) * K;
+                sk.put64((u64)p0 | ((u64)p1 << s2), 2 * s2);
             }
             return;
         }
@@ -226,7 +240,8 @@ TRPX_DEVICE void pack_block12(BitSink& sk, const u32* w, u32 s, u32 cnt)
         if (P::SZ == 4 && s <= 32) {
             const u32 m = s == 32 ? 0xffffffffu : (1u << s) - 1;
 #pragma unroll
-            for (int i = 0; i < 12; ++i) sk.put(w[i] & m, s);
+            for (int i = 0; i < 6; ++i)
+                sk.put64((u64)(w[2 * i] & m) | ((u64)(w[2 * i + 1] & m) << s), 2 * s);
             return;
         }
     }
@@ -249,15 +264,10 @@ TRPX_DEVICE void scan_lengths(u32 len, u32* sm_warp_tot, u32& off, u32& tile_bit
     }
     if (lane == 31) sm_warp_tot[warp] = incl;
     if (named_bar) bar_sync(named_bar, NT); else sync_block();
-    u32 base = 0, total = 0;
-#pragma unroll
-    for (int i = 0; i < NT / 32; ++i) {
-        u32 v = sm_warp_tot[i];
-        if ((u32)i < warp) base += v;
-        total += v;
-    }
+    const u32 wt = lane < (u32)(NT / 32) ? sm_warp_tot[lane] : 0u;    // NT / 32 <= 32 warps
+    const u32 base = warp_add(lane < warp ? wt : 0u);
     off = base + incl - len;
-    tile_bits = total;
+    tile_bits = warp_add(wt);
 }
 
 // Words that several warps may touch (each warp's first word, and the word after the tile's last bit)
@@ -267,7 +277,7 @@ TRPX_DEVICE void zero_boundary_words(u32* stg, u32 off, u32 tile_bits)
 {
     const u32 t = tid();
     if ((t & 31) == 0) stg[off >> 5] = 0;
-    if (t == NT - 1) stg[tile_bits >> 5] = 0;
+    if (t == NT - 1) { stg[tile_bits >> 5] = 0; stg[(tile_bits >> 5) + 1] = 0; }   // partial last word + zero padding
 }
 
 // Resolve the partial words inside a warp without atomics.  OR of disjoint bit fields == ADD, so
@@ -317,8 +327,9 @@ struct TileGeom { u64 frame, tif, group, gfirst_tile; u32 j, m; bool ends, gends
 TRPX_DEVICE TileGeom tile_geom(const EncParams& p, u64 tile)
 {
     TileGeom g;
-    g.frame = tile / p.tiles_per_frame;
-    g.tif = tile % p.tiles_per_frame;
+    const u32 tpf = (u32)p.tiles_per_frame, fr = (u32)tile / tpf;   // n_tiles < 2^31 (plan)
+    g.frame = fr;
+    g.tif = (u32)tile - fr * tpf;
     const u64 gif = g.tif / GROUP;                         // group inside the frame
     g.group = g.frame * p.groups_per_frame + gif;
     g.j = (u32)(g.tif % GROUP);
@@ -396,11 +407,11 @@ TRPX_DEVICE u64 tile_start(const EncParams& p, u64 tile, const TileGeom& g, u32 
 }
 
 // word i of a tile's output window: staging words shifted left by the start position's bit offset
+// (stg[-1] is a zero word, and the word after the tile's last one is zeroed: no bounds checks)
 TRPX_DEVICE u32 window_word(const u32* stg, u32 nstg, u32 i, u32 sh)
 {
-    const u32 lo = (i >= 1 && i - 1 < nstg) ? stg[i - 1] : 0u;
-    const u32 hi = i < nstg ? stg[i] : 0u;
-    return funnel_l(lo, hi, sh);
+    (void)nstg;
+    return funnel_l(stg[(int)i - 1], stg[i], sh);
 }
 
 // The word two neighbouring tiles share is stored by the LATER tile; the earlier one hands its bits of
@@ -478,15 +489,16 @@ TRPX_DEVICE void resolve_and_store(const EncParams& p, u64 tile, u32 tile_bits, 
 
 // ------------------------------------------------------------------ shared-memory layout
 constexpr int ENC_STAGES = 2;       // TMA pixel stages
-constexpr int ENC_SLOTS = 2;        // packed-bit staging slots == resolver warps
+constexpr int ENC_SLOTS = 3;        // packed-bit staging slots == resolver warps
 constexpr int SM_BARS = 0;          // mbarriers, 8 bytes each: full[STAGES], ready[SLOTS], packed[SLOTS], resolved[SLOTS]
-constexpr int SM_TICKETS = 64;      // ENC_STAGES u32
-constexpr int SM_WARP_TOT = 128;    // 32 u32
-constexpr int SM_WARP_LAST = 256;   // 32 u32
-constexpr int SM_BCAST = 384;       // 4 u64 (generic kernel)
-constexpr int SM_MAX = 416;         // u32 running max width
-constexpr int SM_MAIL = 448;        // ENC_SLOTS x {u64 tile, u64 P0, u32 bits, u32 tail_in, u32 tail_out, u32 pad} (32 bytes each)
-constexpr int SM_HEADER = 512;
+constexpr int SM_TICKETS = 128;     // ENC_STAGES u32
+constexpr int SM_WARP_TOT = 256;    // 32 u32
+constexpr int SM_WARP_LAST = 384;   // 32 u32
+constexpr int SM_BCAST = 512;       // 4 u64 (generic kernel)
+constexpr int SM_MAX = 544;         // u32 running max width
+constexpr int SM_MAIL = 576;        // ENC_SLOTS x {u64 tile, u64 P0, u32 bits, u32 tail_in, u32 tail_out, u32 pad} (32 bytes each)
+constexpr int SM_HEADER = 1024;
+static_assert(8 * (ENC_STAGES + 3 * ENC_SLOTS) <= SM_TICKETS && SM_MAIL + 32 * ENC_SLOTS <= SM_HEADER, "shared-memory header layout");
 constexpr u64 TILE_END = ~0ull;
 
 template <typename T, int NT>
@@ -495,7 +507,8 @@ struct EncGeom {
     static constexpr int TILE_BYTES = NT * P::UNIT_BYTES;
     static constexpr int TILE_BLOCKS = NT * P::BPU;
     static constexpr int STAGE_BYTES = ((P::UNIT_BYTES + TILE_BYTES + 127) / 128) * 128;   // halo + tile
-    static constexpr int STG_WORDS = ((TILE_BLOCKS * P::MAXBITS + 31) / 32 + 4 + 3) / 4 * 4;
+    static constexpr int STG_PAD = 4;                        // zero words in front of a slot (window_word reads stg[-1])
+    static constexpr int STG_WORDS = ((TILE_BLOCKS * P::MAXBITS + 31) / 32 + STG_PAD + 4 + 3) / 4 * 4;
     static constexpr int SMEM_BYTES = SM_HEADER + ENC_STAGES * STAGE_BYTES + ENC_SLOTS * STG_WORDS * 4;
     static constexpr int THREADS = NT + 32 * ENC_SLOTS;    // worker warps + resolver warps
 };
@@ -544,15 +557,16 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_SLOTS, 3) terse_encode_kernel(
         }
         mbar_init_fence();
         *sm_max = 0;
+        for (int k = 0; k < ENC_SLOTS; ++k) stg_base[k * G::STG_WORDS + G::STG_PAD - 1] = 0;
     }
     sync_block();
 
     if (t >= (u32)NT) {
         // ================================================================ resolver warp `slot`
         const u32 slot = (t - NT) >> 5;
-        const u32* stg = stg_base + slot * G::STG_WORDS;
+        const u32* stg = stg_base + slot * G::STG_WORDS + G::STG_PAD;
         for (u32 use = 0;; ++use) {
-            mbar_wait(&bar_ready[slot], use & 1);
+            mbar_wait_sleep(&bar_ready[slot], use & 1);    // idle most of the time: do not burn issue slots
             const u64 tile = mail64[slot * 4];
             const u32 tile_bits = mail32[slot * 8 + 4];
             if (tile == TILE_END) break;
@@ -579,7 +593,9 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_SLOTS, 3) terse_encode_kernel(
         const u32 tk = atomic_add(p.ticket, 1u);
         tickets[s] = tk;
         if ((u64)tk < p.n_tiles) {
-            const u64 f = tk / p.tiles_per_frame, tif = tk % p.tiles_per_frame;
+            const u32 tpf = (u32)p.tiles_per_frame;
+            const u64 f = tk / tpf, tif = tk - (u32)f * tpf;
+            tickets[ENC_STAGES + s] = (u32)tif;
             const u64 tile_off = tif * (u64)G::TILE_BYTES;
             u64 bytes = frame_bytes - tile_off;
             if (bytes > (u64)G::TILE_BYTES) bytes = G::TILE_BYTES;
@@ -598,7 +614,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_SLOTS, 3) terse_encode_kernel(
         const u32 pbits = mail32[slot * 8 + 4];
         const TileGeom g = tile_geom(p, ptile);
         const u64 Pn = g.ends ? align_frame(P0 + pbits) : P0 + pbits;
-        store_tile(p, ptile, g, stg_base + slot * G::STG_WORDS, pbits, P0, Pn, mail32[slot * 8 + 5], mail32[slot * 8 + 6], t, NT);
+        store_tile(p, ptile, g, stg_base + slot * G::STG_WORDS + G::STG_PAD, pbits, P0, Pn, mail32[slot * 8 + 5], mail32[slot * 8 + 6], t, NT);
     };
     if (t == 0)
         for (int s = 0; s < ENC_STAGES; ++s) issue(s);
@@ -611,10 +627,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_SLOTS, 3) terse_encode_kernel(
         const u32 slot = it % ENC_SLOTS, use = it / ENC_SLOTS;
         const u64 tile = tickets[s];
         if (tile >= p.n_tiles) break;
-        const u64 tif = tile % p.tiles_per_frame;
-        const u64 first_val = tif * (u64)(G::TILE_BLOCKS * 12);
-        u64 tile_vals = p.n_values - first_val;
-        if (tile_vals > (u64)(G::TILE_BLOCKS * 12)) tile_vals = G::TILE_BLOCKS * 12;
+        const u64 tif = tickets[ENC_STAGES + s];
 
         mbar_wait(&bar_full[s], (it / ENC_STAGES) & 1);
 
@@ -629,15 +642,19 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_SLOTS, 3) terse_encode_kernel(
                 w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
             }
         }
-        const u64 my_first = (u64)t * P::VPU;
-        u32 nvalid = my_first >= tile_vals ? 0u : (tile_vals - my_first > (u64)P::VPU ? (u32)P::VPU : (u32)(tile_vals - my_first));
-        if (nvalid < (u32)P::VPU) {                        // frame tail: wipe what is not ours
-            const u32 vbytes = nvalid * P::SZ;
+        u32 nvalid = P::VPU;
+        if (tif + 1 == p.tiles_per_frame) {                // the frame's last tile may be ragged
+            const u64 tile_vals = p.n_values - tif * (u64)(G::TILE_BLOCKS * 12);
+            const u64 my_first = (u64)t * P::VPU;
+            nvalid = my_first >= tile_vals ? 0u : (tile_vals - my_first > (u64)P::VPU ? (u32)P::VPU : (u32)(tile_vals - my_first));
+            if (nvalid < (u32)P::VPU) {                    // frame tail: wipe what is not ours
+                const u32 vbytes = nvalid * P::SZ;
 #pragma unroll
-            for (int j = 0; j < P::UW; ++j) {
-                const u32 lo = 4u * j;
-                if (vbytes <= lo) w[j] = 0;
-                else if (vbytes < lo + 4) w[j] &= (1u << (8 * (vbytes - lo))) - 1;
+                for (int j = 0; j < P::UW; ++j) {
+                    const u32 lo = 4u * j;
+                    if (vbytes <= lo) w[j] = 0;
+                    else if (vbytes < lo + 4) w[j] &= (1u << (8 * (vbytes - lo))) - 1;
+                }
             }
         }
 
@@ -683,7 +700,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_SLOTS, 3) terse_encode_kernel(
         if (t == 0) st_relaxed(&p.tdesc[tile], TD_VALID | (u64)tile_bits);
 
         // ---- the slot's previous tile goes out (resolved two tile-times ago), then the slot is ours
-        u32* stg = stg_base + slot * G::STG_WORDS;
+        u32* stg = stg_base + slot * G::STG_WORDS + G::STG_PAD;
         if (use > 0) store_slot(slot, use - 1);
         bar_sync(1, NT);                                   // E: slot and mailbox are free
         if (t == 0) {
@@ -732,7 +749,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_SLOTS, 3) terse_encode_kernel(
 // values, the second one hits L1/L2).  Same scan, look-back, staging and store as the fast kernel.
 template <typename T, int NT>
 struct GenGeom {
-    static constexpr int STG_WORDS_MAX = (227 * 1024 - SM_HEADER) / 4 - 8;
+    static constexpr int STG_WORDS_MAX = (227 * 1024 - SM_HEADER) / 4 - 16;
 };
 
 template <typename T>
@@ -751,10 +768,10 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) terse_encode_generic_kernel(EncParams
     u32* sm_warp_last = (u32*)(sm + SM_WARP_LAST);
     u64* bc = (u64*)(sm + SM_BCAST);
     u32* sm_max = (u32*)(sm + SM_MAX);
-    u32* stg = (u32*)(sm + SM_HEADER);
+    u32* stg = (u32*)(sm + SM_HEADER) + 4;                 // stg[-1] is a zero word (window_word)
     const u32 t = tid(), lane = t & 31, warp = t >> 5;
     const u64 tmask = P::W == 64 ? ~0ull : ((1ull << P::W) - 1);
-    if (t == 0) *sm_max = 0;
+    if (t == 0) { *sm_max = 0; stg[-1] = 0; }
     u32 my_max = 0;
     for (;;) {
         sync_block();                                      // previous tile fully stored; tickets reusable
