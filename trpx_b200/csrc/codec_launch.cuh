@@ -148,7 +148,8 @@ inline void encode_async(Launcher& L, int dtype, const void* d_pixels, u64 n_val
     p.tdesc = (u64*)((unsigned char*)scratch + 64);
     p.tails = p.tdesc + pl.n_tiles;
     p.gdesc = p.tails + pl.n_tiles;
-    p.dbg_incl_stride = dbg_incl_stride;
+    p.dbg_incl_stride = dbg_incl_stride & 0xffffu;
+    p.dbg_ring_words = dbg_incl_stride >> 16;
     cudaMemsetAsync(scratch, 0, pl.scratch_bytes, L.stream);
     cudaMemsetAsync(d_prolix_bits, 0, sizeof(u32), L.stream);
     cudaMemsetAsync(d_status, 0, sizeof(u32), L.stream);

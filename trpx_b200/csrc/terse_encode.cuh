@@ -71,7 +71,8 @@ struct EncParams {
     u64* gdesc;             // [n_groups] zeroed: level-2 descriptors (groups of <= 64 tiles of one frame)
     u64* tails;             // [n_tiles] zeroed: boundary-word hand-off
     u32* ticket;            // [1] zeroed
-    u32 dbg_incl_stride;    // tests only: publish INCL for every k-th tile only (0 = always)
+    u32 dbg_incl_stride;    // tests only: publish INCL for every k-th group only (0 = always)
+    u32 dbg_ring_words;     // tests only: capacity of the staging ring in words (0 = EncGeom::RING_WORDS)
 };
 
 // ------------------------------------------------------------------ pixel-type traits
@@ -489,16 +490,18 @@ TRPX_DEVICE void resolve_and_store(const EncParams& p, u64 tile, u32 tile_bits, 
 
 // ------------------------------------------------------------------ shared-memory layout
 constexpr int ENC_STAGES = 2;       // TMA pixel stages
-constexpr int ENC_SLOTS = 3;        // packed-bit staging slots == resolver warps
-constexpr int SM_BARS = 0;          // mbarriers, 8 bytes each: full[STAGES], ready[SLOTS], packed[SLOTS], resolved[SLOTS]
-constexpr int SM_TICKETS = 128;     // ENC_STAGES u32
+constexpr int ENC_DEPTH = 6;        // tiles a CTA may have packed but not yet stored (mailbox entries)
+constexpr int ENC_RESOLVERS = 2;    // resolver warps; resolver r serves iterations it % ENC_RESOLVERS == r
+static_assert(ENC_DEPTH % ENC_RESOLVERS == 0, "a mailbox entry is always served by the same resolver");
+constexpr int SM_BARS = 0;          // mbarriers, 8 bytes each: full[STAGES], ready[DEPTH], packed[DEPTH], resolved[DEPTH]
+constexpr int SM_TICKETS = 192;     // 2 x ENC_STAGES u32: tile, tile-in-frame
 constexpr int SM_WARP_TOT = 256;    // 32 u32
 constexpr int SM_WARP_LAST = 384;   // 32 u32
 constexpr int SM_BCAST = 512;       // 4 u64 (generic kernel)
 constexpr int SM_MAX = 544;         // u32 running max width
-constexpr int SM_MAIL = 576;        // ENC_SLOTS x {u64 tile, u64 P0, u32 bits, u32 tail_in, u32 tail_out, u32 pad} (32 bytes each)
+constexpr int SM_MAIL = 576;        // ENC_DEPTH x {u64 tile, u64 P0, u32 bits, u32 tail_in, u32 tail_out, u32 ring word} (32 bytes each)
 constexpr int SM_HEADER = 1024;
-static_assert(8 * (ENC_STAGES + 3 * ENC_SLOTS) <= SM_TICKETS && SM_MAIL + 32 * ENC_SLOTS <= SM_HEADER, "shared-memory header layout");
+static_assert(8 * (ENC_STAGES + 3 * ENC_DEPTH) <= SM_TICKETS && SM_MAIL + 40 * ENC_DEPTH <= SM_HEADER, "shared-memory header layout");
 constexpr u64 TILE_END = ~0ull;
 
 template <typename T, int NT>
@@ -507,26 +510,30 @@ struct EncGeom {
     static constexpr int TILE_BYTES = NT * P::UNIT_BYTES;
     static constexpr int TILE_BLOCKS = NT * P::BPU;
     static constexpr int STAGE_BYTES = ((P::UNIT_BYTES + TILE_BYTES + 127) / 128) * 128;   // halo + tile
-    static constexpr int STG_PAD = 4;                        // zero words in front of a slot (window_word reads stg[-1])
-    static constexpr int STG_WORDS = ((TILE_BLOCKS * P::MAXBITS + 31) / 32 + STG_PAD + 4 + 3) / 4 * 4;
-    static constexpr int SMEM_BYTES = SM_HEADER + ENC_STAGES * STAGE_BYTES + ENC_SLOTS * STG_WORDS * 4;
-    static constexpr int THREADS = NT + 32 * ENC_SLOTS;    // worker warps + resolver warps
+    // Packed tiles wait in a ring of words until their stream position is known.  A tile takes
+    // (bits / 32 + 1) words plus a zero word on either side (window_word), rounded to 4: ~0.7 K words
+    // for a typical 512^2 u16 tile, WORST_WORDS when nothing compresses.  The ring always holds two
+    // worst-case tiles; with typical data ENC_DEPTH tiles are in flight.
+    static constexpr int WORST_WORDS = ((TILE_BLOCKS * P::MAXBITS + 31) / 32 + 1 + 2 + 3) / 4 * 4;
+    static constexpr int RING_WORDS = 2 * WORST_WORDS > 9216 ? 2 * WORST_WORDS : 9216;
+    static constexpr int SMEM_BYTES = SM_HEADER + ENC_STAGES * STAGE_BYTES + RING_WORDS * 4;
+    static constexpr int THREADS = NT + 32 * ENC_RESOLVERS;   // worker warps + resolver warps
 };
 
 // ------------------------------------------------------------------ fast kernel: block == 12, 16-byte aligned frames
 // Warp-specialised persistent CTA.
 //   workers (NT threads)   wait for a TMA-staged tile, keep their 48 bytes in registers, compute widths /
-//                          headers / lengths, scan, publish the tile's bit count, pack into a staging slot
-//                          in tile-relative coordinates.  The slot's PREVIOUS tile (two iterations ago) is
-//                          stored first -- shifted into place, coalesced streaming stores -- by which time
-//                          its stream position has long been resolved, so workers never wait for global
-//                          memory round trips; their blocking points are the TMA full-barrier (prefetched
-//                          two tiles ahead) and that resolution.
-//   resolvers (1 warp per staging slot, alternating tiles)
+//                          headers / lengths, scan, publish the tile's bit count, and pack the tile into
+//                          the staging ring in tile-relative coordinates.  Packed tiles are stored --
+//                          shifted into place, coalesced streaming stores -- up to ENC_DEPTH iterations
+//                          later, by which time their stream position has long been resolved: workers
+//                          never wait for a global-memory round trip.  Their blocking points are the TMA
+//                          full-barrier (prefetched two tiles ahead) and a resolution that is really late.
+//   resolvers (ENC_RESOLVERS warps, alternating tiles)
 //                          find the tile's stream position with the two-level look-back and exchange the
 //                          boundary word with the neighbour tile: pure latency, off the workers' path.
 template <typename T, int NT>
-TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_SLOTS, 3) terse_encode_kernel(EncParams p)
+TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_RESOLVERS, 3) terse_encode_kernel(EncParams p)
 {
     typedef Pix<T> P;
     typedef EncGeom<T, NT> G;
@@ -534,53 +541,55 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_SLOTS, 3) terse_encode_kernel(
     u64* bars = (u64*)(sm + SM_BARS);
     u64* bar_full = bars;
     u64* bar_ready = bars + ENC_STAGES;
-    u64* bar_packed = bar_ready + ENC_SLOTS;
-    u64* bar_resolved = bar_packed + ENC_SLOTS;
+    u64* bar_packed = bar_ready + ENC_DEPTH;
+    u64* bar_resolved = bar_packed + ENC_DEPTH;
     u32* tickets = (u32*)(sm + SM_TICKETS);
+    u32* vbases = (u32*)(sm + SM_TICKETS + 32);                         // [ENC_DEPTH] virtual ring offset of a pending tile
+    volatile u64* pn64 = (volatile u64*)(sm + SM_MAIL + 32 * ENC_DEPTH);  // [ENC_DEPTH] end position of a resolved tile
     u32* sm_warp_tot = (u32*)(sm + SM_WARP_TOT);
     u32* sm_warp_last = (u32*)(sm + SM_WARP_LAST);
     u32* sm_max = (u32*)(sm + SM_MAX);
-    volatile u64* mail64 = (volatile u64*)(sm + SM_MAIL);               // [slot * 4 + {0: tile, 1: P0}]
-    volatile u32* mail32 = (volatile u32*)(sm + SM_MAIL);               // [slot * 8 + {4: bits, 5: tail_in, 6: tail_out}]
+    volatile u64* mail64 = (volatile u64*)(sm + SM_MAIL);               // [e * 4 + {0: tile, 1: P0}]
+    volatile u32* mail32 = (volatile u32*)(sm + SM_MAIL);               // [e * 8 + {4: bits, 5: tail_in, 6: tail_out, 7: ring word}]
     unsigned char* stages = sm + SM_HEADER;
-    u32* stg_base = (u32*)(stages + ENC_STAGES * G::STAGE_BYTES);
+    u32* ring = (u32*)(stages + ENC_STAGES * G::STAGE_BYTES);
 
     const u32 t = tid(), lane = t & 31, warp = t >> 5;
     const u64 frame_bytes = p.n_values * P::SZ;
 
     if (t == 0) {
         for (int s = 0; s < ENC_STAGES; ++s) mbar_init(&bar_full[s], 1);
-        for (int s = 0; s < ENC_SLOTS; ++s) {
-            mbar_init(&bar_ready[s], 1);
-            mbar_init(&bar_packed[s], NT);
-            mbar_init(&bar_resolved[s], 1);
+        for (int e = 0; e < ENC_DEPTH; ++e) {
+            mbar_init(&bar_ready[e], 1);
+            mbar_init(&bar_packed[e], NT);
+            mbar_init(&bar_resolved[e], 1);
         }
         mbar_init_fence();
         *sm_max = 0;
-        for (int k = 0; k < ENC_SLOTS; ++k) stg_base[k * G::STG_WORDS + G::STG_PAD - 1] = 0;
     }
     sync_block();
 
     if (t >= (u32)NT) {
-        // ================================================================ resolver warp `slot`
-        const u32 slot = (t - NT) >> 5;
-        const u32* stg = stg_base + slot * G::STG_WORDS + G::STG_PAD;
-        for (u32 use = 0;; ++use) {
-            mbar_wait_sleep(&bar_ready[slot], use & 1);    // idle most of the time: do not burn issue slots
-            const u64 tile = mail64[slot * 4];
-            const u32 tile_bits = mail32[slot * 8 + 4];
+        // ================================================================ resolver warp r
+        for (u32 it = (t - NT) >> 5;; it += ENC_RESOLVERS) {
+            const u32 e = it % ENC_DEPTH, use = it / ENC_DEPTH;
+            mbar_wait_sleep(&bar_ready[e], use & 1);       // idle most of the time: do not burn issue slots
+            const u64 tile = mail64[e * 4];
+            const u32 tile_bits = mail32[e * 8 + 4];
             if (tile == TILE_END) break;
+            const u32* stg = ring + mail32[e * 8 + 7];
             const TileGeom g = tile_geom(p, tile);
             const u64 P0 = tile_start(p, tile, g, tile_bits, false);
             const u64 Pn = g.ends ? align_frame(P0 + tile_bits) : P0 + tile_bits;
-            mbar_wait(&bar_packed[slot], use & 1);         // the workers' staging stores are visible now
+            mbar_wait(&bar_packed[e], use & 1);            // the workers' staging stores are visible now
             if (lane == 0) {
                 u32 tout;
                 const u32 tin = tail_handoff(p, tile, stg, tile_bits, P0, Pn, tout);
-                mail64[slot * 4 + 1] = P0;
-                mail32[slot * 8 + 5] = tin;
-                mail32[slot * 8 + 6] = tout;
-                mbar_arrive(&bar_resolved[slot]);
+                mail64[e * 4 + 1] = P0;
+                mail32[e * 8 + 5] = tin;
+                mail32[e * 8 + 6] = tout;
+                pn64[e] = Pn;
+                mbar_arrive(&bar_resolved[e]);
             }
             sync_warp();
         }
@@ -606,25 +615,31 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_SLOTS, 3) terse_encode_kernel(
             bulk_g2s(dst, src, (u32)bytes, &bar_full[s]);
         }
     };
-    // store the tile that occupies staging slot `slot` (its `use`-th tile), once resolved
-    auto store_slot = [&](u32 slot, u32 use) {
-        mbar_wait(&bar_resolved[slot], use & 1);
-        const u64 ptile = mail64[slot * 4];
-        const u64 P0 = mail64[slot * 4 + 1];
-        const u32 pbits = mail32[slot * 8 + 4];
-        const TileGeom g = tile_geom(p, ptile);
-        const u64 Pn = g.ends ? align_frame(P0 + pbits) : P0 + pbits;
-        store_tile(p, ptile, g, stg_base + slot * G::STG_WORDS + G::STG_PAD, pbits, P0, Pn, mail32[slot * 8 + 5], mail32[slot * 8 + 6], t, NT);
+    // store the tile packed in iteration `j`, once resolved
+    auto store_pending = [&](u32 j) {
+        const u32 e = j % ENC_DEPTH;
+        mbar_wait(&bar_resolved[e], (j / ENC_DEPTH) & 1);
+        const u64 ptile = mail64[e * 4];
+        const u64 P0 = mail64[e * 4 + 1], Pn = pn64[e];
+        const u32 pbits = mail32[e * 8 + 4];
+        TileGeom g;
+        if (t == 0) g = tile_geom(p, ptile);               // only rank 0 needs the frame bookkeeping
+        else { g.frame = 0; g.ends = false; }
+        store_tile(p, ptile, g, ring + mail32[e * 8 + 7], pbits, P0, Pn, mail32[e * 8 + 5], mail32[e * 8 + 6], t, NT);
     };
     if (t == 0)
         for (int s = 0; s < ENC_STAGES; ++s) issue(s);
     bar_sync(1, NT);
 
+    // ring bookkeeping, identical in every worker thread: virtual word offsets that only grow; the
+    // tiles of iterations [oldest, it) are packed but not stored and occupy [vtail, vhead)
+    u32 vhead = 0, vtail = 0, oldest = 0;
+    const u32 ring_words = p.dbg_ring_words ? p.dbg_ring_words : (u32)G::RING_WORDS;   // tests shrink the ring
     u32 my_max = 0;
     u32 it = 0;
     for (;; ++it) {
         const int s = (int)(it % ENC_STAGES);
-        const u32 slot = it % ENC_SLOTS, use = it / ENC_SLOTS;
+        const u32 e = it % ENC_DEPTH;
         const u64 tile = tickets[s];
         if (tile >= p.n_tiles) break;
         const u64 tif = tickets[ENC_STAGES + s];
@@ -699,15 +714,29 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_SLOTS, 3) terse_encode_kernel(
         // publish the tile's bit count at once: other tiles' look-backs must never wait for our resolver
         if (t == 0) st_relaxed(&p.tdesc[tile], TD_VALID | (u64)tile_bits);
 
-        // ---- the slot's previous tile goes out (resolved two tile-times ago), then the slot is ours
-        u32* stg = stg_base + slot * G::STG_WORDS + G::STG_PAD;
-        if (use > 0) store_slot(slot, use - 1);
-        bar_sync(1, NT);                                   // E: slot and mailbox are free
-        if (t == 0) {
-            mail64[slot * 4] = tile;
-            mail32[slot * 8 + 4] = tile_bits;
-            mbar_arrive(&bar_ready[slot]);                 // the resolver may start its look-back
+        // ---- room in the ring: physically contiguous, one zero word in front (window_word reads stg[-1])
+        const u32 need = ((tile_bits >> 5) + 1 + 2 + 3) & ~3u;
+        u32 vbase = vhead;
+        if (vbase % ring_words + need > ring_words) vbase += ring_words - vbase % ring_words;
+        bool stored = false;
+        while (it - oldest == (u32)ENC_DEPTH || (it > oldest && vbase + need - vtail > ring_words)) {
+            store_pending(oldest);                         // blocks only if that resolution is really late
+            ++oldest;
+            vtail = oldest < it ? vbases[oldest % ENC_DEPTH] : vbase;   // virtual base of the next pending tile
+            stored = true;
         }
+        if (stored) bar_sync(1, NT);                       // E: freed ring words and mailbox entries are reusable
+        u32* stg = ring + vbase % ring_words + 1;
+        if (t == 0) {
+            mail64[e * 4] = tile;
+            vbases[e] = vbase;
+            mail32[e * 8 + 4] = tile_bits;
+            mail32[e * 8 + 7] = vbase % ring_words + 1;
+            stg[-1] = 0;
+            mbar_arrive(&bar_ready[e]);                    // the resolver may start its look-back
+        }
+        vhead = vbase + need;
+        if (it == oldest) vtail = vbase;
         zero_boundary_words<NT>(stg, off, tile_bits);
         bar_sync(1, NT);                                   // C
 
@@ -721,21 +750,18 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_SLOTS, 3) terse_encode_kernel(
                 pack_block12<T>(sk, &w[b * P::BW], sb[b], cnt[b]);
             }
         merge_and_flush(sk, off + len);
-        mbar_arrive(&bar_packed[slot]);                    // D: all NT workers arrive -> staging complete
+        mbar_arrive(&bar_packed[e]);                       // D: all NT workers arrive -> staging complete
         // Shared scratch reused by the next iteration is rewritten only after one of its barriers
         // A..C, which no worker passes before all have finished reading this iteration's values.
     }
-    // drain: the last tiles still sitting in the staging slots, oldest first
-    for (u32 k = (it < (u32)ENC_SLOTS ? it : (u32)ENC_SLOTS); k >= 1; --k) {
-        const u32 j = it - k;
-        store_slot(j % ENC_SLOTS, j / ENC_SLOTS);
-    }
+    // drain: the tiles still waiting in the ring, oldest first
+    for (; oldest < it; ++oldest) store_pending(oldest);
     bar_sync(1, NT);
-    // tell both resolvers that there is nothing more
+    // tell the resolvers that there is nothing more: the next iteration each of them would serve
     if (t == 0) {
-        for (u32 slot = 0; slot < (u32)ENC_SLOTS; ++slot) {
-            mail64[slot * 4] = TILE_END;
-            mbar_arrive(&bar_ready[slot]);
+        for (u32 k = 0; k < (u32)ENC_RESOLVERS; ++k) {
+            mail64[((it + k) % ENC_DEPTH) * 4] = TILE_END;
+            mbar_arrive(&bar_ready[(it + k) % ENC_DEPTH]);
         }
     }
     my_max = warp_max(my_max);
