@@ -33,7 +33,14 @@ struct Launcher {
     void (*mark_fn)(void* user, const char* name) = nullptr;
     void* mark_user = nullptr;
     void mark(const char* name) { if (mark_fn) mark_fn(mark_user, name); }
-    void count(const char* name) { if (launches) ++*launches; mark(name); }
+    void count(const char* name)
+    {
+#ifdef TRPX_EMU_TRACE
+        fprintf(stderr, "emu: kernel %s done\n", name);
+#endif
+        if (launches) ++*launches;
+        mark(name);
+    }
 };
 
 // ---------------------------------------------------------------------------------- encode
@@ -167,7 +174,7 @@ inline void encode_async(Launcher& L, int dtype, const void* d_pixels, u64 n_val
 }
 
 // ---------------------------------------------------------------------------------- decode
-constexpr int WALK_NT = 64;       // threads per CTA of the P1 walkers (one stream segment per thread)
+constexpr int WALK_NT = 128;      // threads per CTA of the P1 walkers (one stream segment per thread)
 constexpr int RESOLVE_NT = 256;   // threads per CTA of the cooperative verify / scan kernel
 constexpr int SEGTAB_NT = 1024;
 
@@ -198,6 +205,8 @@ inline DecPlan dec_plan(int out_dtype, u64 payload_bytes, u64 n_values, u64 n_fr
     pl.staged = block == 12 && ((uintptr_t)d_out & 15) == 0 && ((n_values * so) & 15) == 0;
     pl.seg_bytes = seg_bytes < 16 ? 16 : seg_bytes;
     pl.warm_bytes = warm_bytes;
+    // the walkers keep lane-relative bit positions in 32 bits
+    if ((u64)pl.seg_bytes + warm_bytes >= (1ull << 27) || (u64)block * 73 + 12 >= (1ull << 31)) pl.ok = false;
     pl.max_segs = payload_bytes / pl.seg_bytes + n_frames + 1;
     pl.smem_unpack = 128 + DEC_TB + 16 + (size_t)DEC_TB * 4 + (pl.staged ? (size_t)DEC_TB * 12 * so : 0);
     size_t o = 0;
@@ -294,13 +303,14 @@ inline void decode_async(Launcher& L, const void* d_payload, u64 payload_bytes, 
     L.count("prolix_segments");
     if (L.err != cudaSuccess) return;
     const u32 walk_grid = (u32)div_up(pl.max_segs, WALK_NT);
-    L.err = launch(prolix_walk_kernel<WALK_NT>, walk_grid, (u32)WALK_NT, 0, L.stream, p);
+    const size_t walk_smem = (size_t)(WALK_NT / 32) * WALK_BUF_WORDS * 4;
+    L.err = launch(prolix_walk_kernel<WALK_NT>, walk_grid, (u32)WALK_NT, walk_smem, L.stream, p);
     L.count("prolix_walk");
     if (L.err != cudaSuccess) return;
     L.err = launch_coop(prolix_resolve_kernel<RESOLVE_NT>, coop_grid, (u32)RESOLVE_NT, 0, L.stream, p);
     L.count("prolix_resolve");
     if (L.err != cudaSuccess) return;
-    L.err = launch(prolix_emit_kernel<WALK_NT>, walk_grid, (u32)WALK_NT, 0, L.stream, p);
+    L.err = launch(prolix_emit_kernel<WALK_NT>, walk_grid, (u32)WALK_NT, walk_smem, L.stream, p);
     L.count("prolix_emit");
     if (L.err != cudaSuccess) return;
     if (is_signed) unpack_launch<true>(L, out_dtype, pl, p);

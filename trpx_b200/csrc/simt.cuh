@@ -57,6 +57,7 @@ TRPX_DEVICE u32 ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 TRPX_DEVICE bool all_lanes(bool p) { return __all_sync(0xffffffffu, p); }
 TRPX_DEVICE bool any_lane(bool p) { return __any_sync(0xffffffffu, p); }
 TRPX_DEVICE u32 warp_max(u32 v) { return __reduce_max_sync(0xffffffffu, v); }
+TRPX_DEVICE u32 warp_min_u32(u32 v) { return __reduce_min_sync(0xffffffffu, v); }
 TRPX_DEVICE u32 warp_or(u32 v) { return __reduce_or_sync(0xffffffffu, v); }
 TRPX_DEVICE u32 warp_add(u32 v) { return __reduce_add_sync(0xffffffffu, v); }
 
@@ -222,6 +223,7 @@ inline u32 ballot(bool p) { return ::emu::ballot(p); }
 inline bool all_lanes(bool p) { return ::emu::ballot(p) == ::emu::ballot(true); }
 inline bool any_lane(bool p) { return ::emu::ballot(p) != 0; }
 inline u32 warp_max(u32 v) { return ::emu::warp_reduce(v, 0); }
+inline u32 warp_min_u32(u32 v) { return ~::emu::warp_reduce(~v, 0); }
 inline u32 warp_or(u32 v) { return ::emu::warp_reduce(v, 1); }
 inline u32 warp_add(u32 v) { return ::emu::warp_reduce(v, 2); }
 
