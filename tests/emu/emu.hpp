@@ -24,6 +24,8 @@ enum { cudaSuccess = 0 };
 
 struct alignas(16) uint4 { uint32_t x, y, z, w; };
 inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+struct alignas(8) uint2 { uint32_t x, y; };
+inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
 
 struct ThreadCtx { uint32_t tid, bid, block_dim, grid_dim; };
 

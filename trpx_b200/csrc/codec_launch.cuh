@@ -179,10 +179,10 @@ constexpr int RESOLVE_NT = 256;   // threads per CTA of the cooperative verify /
 constexpr int SEGTAB_NT = 1024;
 
 struct DecPlan {
-    bool staged;                  // block == 12 and 16-byte aligned frames: TMA-store unpack kernel
+    bool staged;                  // block == 12 and 16-byte aligned frames: fused re-walk + unpack kernel (TMA store)
     u64 nblocks, tiles_per_frame, n_tiles, max_segs;
-    u32 last_cnt, seg_bytes, warm_bytes;
-    size_t smem_unpack;
+    u32 last_cnt, seg_bytes, warm_bytes, subs_per_seg;
+    size_t smem_unpack, off_ckpt;
     // scratch layout (byte offsets)
     size_t off_frame_ends, off_seg_base, off_seg_frame, off_seg_entry, off_seg_exit, off_seg_count,
         off_seg_b0, off_changed, off_zero_begin, off_widths, off_anchors, scratch_bytes;
@@ -203,12 +203,13 @@ inline DecPlan dec_plan(int out_dtype, u64 payload_bytes, u64 n_values, u64 n_fr
     pl.n_tiles = pl.tiles_per_frame * n_frames;
     if (pl.n_tiles >= (1ull << 31)) pl.ok = false;
     pl.staged = block == 12 && ((uintptr_t)d_out & 15) == 0 && ((n_values * so) & 15) == 0;
-    pl.seg_bytes = seg_bytes < 16 ? 16 : seg_bytes;
+    pl.seg_bytes = (seg_bytes < SUB_BYTES ? SUB_BYTES : seg_bytes + SUB_BYTES - 1) / SUB_BYTES * SUB_BYTES;
+    pl.subs_per_seg = pl.seg_bytes / SUB_BYTES;
     pl.warm_bytes = warm_bytes;
     // the walkers keep lane-relative bit positions in 32 bits
-    if ((u64)pl.seg_bytes + warm_bytes >= (1ull << 27) || (u64)block * 73 + 12 >= (1ull << 31)) pl.ok = false;
+    if ((u64)pl.seg_bytes + warm_bytes >= (1ull << 19) || (u64)block * 73 + 12 >= (1ull << 23)) pl.ok = false;
     pl.max_segs = payload_bytes / pl.seg_bytes + n_frames + 1;
-    pl.smem_unpack = 128 + DEC_TB + 16 + (size_t)DEC_TB * 4 + (pl.staged ? (size_t)DEC_TB * 12 * so : 0);
+    pl.smem_unpack = 128 + DEC_TB + 16 + (size_t)DEC_TB * 4;
     size_t o = 0;
     pl.off_frame_ends = o; o = align_up(o + n_frames * 8, 256);
     pl.off_seg_base = o;   o = align_up(o + (n_frames + 1) * 8, 256);
@@ -219,8 +220,14 @@ inline DecPlan dec_plan(int out_dtype, u64 payload_bytes, u64 n_values, u64 n_fr
     pl.off_seg_b0 = o;     o = align_up(o + pl.max_segs * 8, 256);
     pl.off_zero_begin = o;                                   // everything from here is zeroed per call
     pl.off_changed = o;    o = align_up(o + 16, 256);
-    pl.off_anchors = o;    o = align_up(o + pl.n_tiles * 8, 256);
-    pl.off_widths = o;     o = align_up(o + n_frames * pl.nblocks + 16, 256);
+    if (pl.staged) {                                         // fast path: checkpoints instead of widths + anchors
+        pl.off_ckpt = o;   o = align_up(o + pl.max_segs * pl.subs_per_seg * 8, 256);
+        pl.off_anchors = pl.off_widths = o;
+    } else {
+        pl.off_ckpt = o;
+        pl.off_anchors = o; o = align_up(o + pl.n_tiles * 8, 256);
+        pl.off_widths = o;  o = align_up(o + n_frames * pl.nblocks + 16, 256);
+    }
     pl.scratch_bytes = o;
     return pl;
 }
@@ -228,11 +235,14 @@ inline DecPlan dec_plan(int out_dtype, u64 payload_bytes, u64 n_values, u64 n_fr
 template <typename O, bool SGN>
 inline void unpack_launch_t(Launcher& L, const DecPlan& pl, const DecParams& p)
 {
-    if (pl.staged)
-        L.err = launch(prolix_unpack_kernel<O, SGN, true>, (u32)pl.n_tiles, DEC_NT, pl.smem_unpack, L.stream, p);
-    else
+    if (pl.staged) {
+        const u64 grid = pl.max_segs * div_up(pl.subs_per_seg, UNP_NT);
+        L.err = launch(prolix_unpack_seg_kernel<O, SGN>, (u32)grid, (u32)UNP_NT, (size_t)UNP_SMEM_BYTES, L.stream, p);
+        L.count("prolix_unpack_seg");
+    } else {
         L.err = launch(prolix_unpack_kernel<O, SGN, false>, (u32)pl.n_tiles, DEC_NT, pl.smem_unpack, L.stream, p);
-    L.count("prolix_unpack");
+        L.count("prolix_unpack");
+    }
 }
 template <bool SGN>
 inline void unpack_launch(Launcher& L, int out_dtype, const DecPlan& pl, const DecParams& p)
@@ -279,12 +289,15 @@ inline void decode_async(Launcher& L, const void* d_payload, u64 payload_bytes, 
     p.changed = (u32*)(sc + pl.off_changed);
     p.widths = sc + pl.off_widths;
     p.anchors = (u64*)(sc + pl.off_anchors);
+    p.ckpt = pl.staged ? (u64*)(sc + pl.off_ckpt) : nullptr;
+    p.subs_per_seg = pl.subs_per_seg;
     p.tile_blocks = DEC_TB;
     p.tiles_per_frame = pl.tiles_per_frame;
     p.out = d_out;
     p.status = d_status;
     cudaMemsetAsync(d_status, 0, sizeof(u32), L.stream);
-    cudaMemsetAsync(sc + pl.off_zero_begin, 0, pl.scratch_bytes - pl.off_zero_begin, L.stream);
+    // the fix-up flags always; widths (pre-zeroed: empty blocks are never written) and anchors on the generic path
+    cudaMemsetAsync(sc + pl.off_zero_begin, 0, pl.staged ? 256 : pl.scratch_bytes - pl.off_zero_begin, L.stream);
     L.mark("memset");
     if (d_frame_ends == nullptr) {
         u64* fe = d_frame_ends_out ? d_frame_ends_out : (u64*)(sc + pl.off_frame_ends);
@@ -310,9 +323,11 @@ inline void decode_async(Launcher& L, const void* d_payload, u64 payload_bytes, 
     L.err = launch_coop(prolix_resolve_kernel<RESOLVE_NT>, coop_grid, (u32)RESOLVE_NT, 0, L.stream, p);
     L.count("prolix_resolve");
     if (L.err != cudaSuccess) return;
-    L.err = launch(prolix_emit_kernel<WALK_NT>, walk_grid, (u32)WALK_NT, walk_smem, L.stream, p);
-    L.count("prolix_emit");
-    if (L.err != cudaSuccess) return;
+    if (!pl.staged) {
+        L.err = launch(prolix_emit_kernel<WALK_NT>, walk_grid, (u32)WALK_NT, walk_smem, L.stream, p);
+        L.count("prolix_emit");
+        if (L.err != cudaSuccess) return;
+    }
     if (is_signed) unpack_launch<true>(L, out_dtype, pl, p);
     else unpack_launch<false>(L, out_dtype, pl, p);
 }

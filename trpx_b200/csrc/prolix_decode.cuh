@@ -47,6 +47,9 @@ struct DecParams {
     u32* seg_count;         // [max_segs] headers that start inside the segment
     u64* seg_b0;            // [max_segs] index of the segment's first block inside its frame
     u32* changed;           // [3] rotating sweep flags of the fix-up loop (zeroed)
+    // P1 -> fused P2: exact checkpoints, one per SUB_BYTES of every segment (nullptr on the generic path)
+    u64* ckpt;              // [max_segs * subs_per_seg]: first header at or after the sub-segment's first bit
+    u32 subs_per_seg;
     // P1 -> P2
     unsigned char* widths;  // [n_frames * nblocks], zeroed
     u64* anchors;           // [n_frames * tiles_per_frame] frame-relative bit of each tile's first header
@@ -107,6 +110,42 @@ struct StreamWindow {
     }
 };
 
+// Checkpoint of a 64-byte sub-segment: the first header at or after its first bit, as
+// (bit offset from the segment's start : 24 | width carried into that header : 8 | headers of the segment before it : 32).
+constexpr u32 SUB_BYTES = 64, SUB_BITS = SUB_BYTES * 8, SUB_SHIFT = 9;
+TRPX_HD u64 pack_ckpt(u32 rel, u32 s, u32 n) { return ((u64)rel << 40) | ((u64)(s & 0xff) << 32) | (u64)n; }
+TRPX_HD u32 ckpt_rel(u64 c) { return (u32)(c >> 40); }
+TRPX_HD u32 ckpt_s(u64 c) { return (u32)(c >> 32) & 0xff; }
+TRPX_HD u32 ckpt_n(u64 c) { return (u32)c; }
+
+// Records the checkpoints of ONE segment while its headers are visited in order.  `rel` is the
+// header's bit offset from the segment's start.
+struct CkptSink {
+    u64* row;               // this segment's checkpoints (nullptr: record nothing)
+    u32 subs, next_m;
+    TRPX_DEVICE void init(u64* row_, u32 subs_) { row = row_; subs = subs_; next_m = 0; }
+    TRPX_DEVICE void at(u32 rel, u32 s_prev, u32 n)          // a header starts at rel
+    {
+        if (!row) return;
+        const u32 m = rel >> SUB_SHIFT;
+        while (next_m <= m && next_m < subs) row[next_m++] = pack_ckpt(rel, s_prev, n);
+    }
+    TRPX_DEVICE void run(u32 rel, u32 n, u32 len)            // len one-bit headers (width 0) from rel
+    {
+        if (!row) return;
+        at(rel, 0, n);
+        while (next_m < subs && (next_m << SUB_SHIFT) < rel + len) {   // boundaries inside the run are headers themselves
+            const u32 r2 = next_m << SUB_SHIFT;
+            row[next_m++] = pack_ckpt(r2, 0, n + (r2 - rel));
+        }
+    }
+    TRPX_DEVICE void finish(u32 rel_exit, u32 s_exit, u32 n)  // sub-segments in which no header starts any more
+    {
+        if (!row) return;
+        while (next_m < subs) row[next_m++] = pack_ckpt(rel_exit, s_exit, n);
+    }
+};
+
 // Walk block headers from (pos, s) while pos < stop; all positions are bits relative to the frame,
 // base_bit is the frame's first bit in the payload.  Returns the number of headers visited.
 // Runs of '1' headers with width 0 (all-zero blocks, 1 bit each) are skipped a word at a time.
@@ -116,7 +155,7 @@ struct NoSink {
 };
 template <class Sink>
 TRPX_DEVICE u64 walk_headers(const u32* payload, u64 n_words, u64 base_bit, u32 block, u64& pos, u32& s,
-                             u64 stop, Sink& sink)
+                             u64 stop, Sink& sink, CkptSink* ck = nullptr, u64 seg_r0 = 0)
 {
     u64 n = 0;
     StreamWindow sw;
@@ -127,15 +166,18 @@ TRPX_DEVICE u64 walk_headers(const u32* payload, u64 n_words, u64 base_bit, u32 
             u64 run = (u64)ffs64(~win | (1ull << 63)) - 1;       // consecutive '1' headers (<= 63)
             if (run > stop - pos) run = stop - pos;
             sink.zeros(n, pos, run);
+            if (ck) ck->run((u32)(pos - seg_r0), (u32)n, (u32)run);
             n += run;
             pos += run;
             continue;
         }
+        if (ck) ck->at((u32)(pos - seg_r0), s, (u32)n);
         const u32 hl = decode_header(win, s);
         sink.block(n, pos, s);
         pos += hl + (u64)s * block;
         ++n;
     }
+    if (ck) ck->finish((u32)(pos - seg_r0), s, (u32)n);
     return n;
 }
 
@@ -200,7 +242,7 @@ TRPX_DEVICE void walk_stage(u32* buf, const uint4 (&pre)[8])
 // All 32 lanes of a warp call this together.  sink.block(k, q, s) / sink.zeros(k, q, run) see the k-th
 // header after the entry at lane-relative bit q.
 template <class Sink>
-TRPX_DEVICE void warp_walk(const DecParams& p, u32* buf, WalkLane& L, Sink& sink)
+TRPX_DEVICE void warp_walk(const DecParams& p, u32* buf, WalkLane& L, Sink& sink, CkptSink& ck)
 {
     const u32 lane = tid() & 31;
     const u32 my_rounds = L.have ? ((L.qB + 31) >> 5) / WALK_ROUND_STRIDE + 1 : 0u;
@@ -229,10 +271,11 @@ TRPX_DEVICE void warp_walk(const DecParams& p, u32* buf, WalkLane& L, Sink& sink
                     u32 run = (u32)ffs32(~win) - 1;          // ffs32(0) == 0 -> 0xffffffff: all 32 bits set
                     if (run > 32u) run = 32u;
                     if (run > stop - L.q) run = stop - L.q;
-                    if (L.entered) sink.zeros(L.n, L.q, run);
+                    if (L.entered) { sink.zeros(L.n, L.q, run); ck.run(L.q - L.qA, (u32)L.n, run); }
                     L.n += run;
                     L.q += run;
                 } else {
+                    if (L.entered) ck.at(L.q - L.qA, L.s, (u32)L.n);
                     const u32 hl = decode_header((u64)win, L.s);
                     if (L.entered) sink.block(L.n, L.q, L.s);
                     L.q += hl + L.s * p.block;
@@ -330,9 +373,12 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_walk_kernel(DecParams p)
         L.qB = (u32)(g.r1 - delta);
     }
     NoSink ns;
-    warp_walk(p, buf, L, ns);
+    CkptSink ck;
+    ck.init(L.have && p.ckpt ? p.ckpt + j * p.subs_per_seg : nullptr, p.subs_per_seg);
+    warp_walk(p, buf, L, ns, ck);
     if (L.have) {
         if (!L.entered) { L.q_entry = L.q; L.s_entry = L.s; L.n = 0; }   // the warm-up jumped over the whole segment
+        ck.finish(L.q - L.qA, L.s, (u32)L.n);
         p.seg_entry[j] = pack_state(L.q_entry + delta, L.s_entry);
         p.seg_exit[j] = pack_state(L.q + delta, L.s);
         p.seg_count[j] = L.n > 0xffffffffull ? 0xffffffffu : (u32)L.n;
@@ -371,7 +417,9 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_resolve_kernel(DecParams p)
             u64 pos = state_pos(want);
             u32 s = state_s(want);
             p.seg_entry[j] = want;
-            const u64 n = walk_headers(p.payload, n_words, g.base_bit, p.block, pos, s, g.r1, ns);
+            CkptSink ck;
+            ck.init(p.ckpt ? p.ckpt + j * p.subs_per_seg : nullptr, p.subs_per_seg);
+            const u64 n = walk_headers(p.payload, n_words, g.base_bit, p.block, pos, s, g.r1, ns, &ck, g.r0);
             st_relaxed(&p.seg_exit[j], pack_state(pos, s));
             p.seg_count[j] = n > 0xffffffffull ? 0xffffffffu : (u32)n;
             atomic_or(flag, 1u);
@@ -491,7 +539,9 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_emit_kernel(DecParams p)
             sink.frame = g.frame; sink.b0 = b0; sink.delta = delta;
         }
     }
-    warp_walk(p, buf, L, sink);
+    CkptSink ck;
+    ck.init(nullptr, 0);
+    warp_walk(p, buf, L, sink, ck);
     if (L.have) {
         sink.flush();
         if (sink.bad) atomic_max(p.status, DEC_MALFORMED);
@@ -656,6 +706,219 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(DEC_NT, 1) prolix_unpack_kernel(DecParams p)
             bulk_commit();
             bulk_wait_read0();
         }
+    }
+}
+
+// ------------------------------------------------------------------ P2 (fast path): re-walk 64-byte sub-segments and unpack
+// One thread per sub-segment: from its exact checkpoint it reads headers and values with ONE
+// sequential bit reader over shared memory (the CTA's slice of the stream is staged there with a
+// 17-word pitch per 16 words, so that lanes 64 bytes apart hit different banks), and writes whole
+// blocks into an output stage in block order.  The stage leaves with one TMA bulk store.  No widths
+// array, no second header pass over global memory.
+constexpr int UNP_NT = 128;                              // sub-segments (threads) per CTA: 8 KB of stream
+constexpr u32 UNP_TAIL_WORDS = 64;                       // a block that starts in the slice ends inside this tail
+constexpr u32 UNP_SPAN_WORDS = UNP_NT * (SUB_BYTES / 4) + UNP_TAIL_WORDS + 4;
+constexpr u32 UNP_SPAN_PADDED = UNP_SPAN_WORDS + UNP_SPAN_WORDS / 16 + 4;
+constexpr u32 UNP_STAGE_BYTES = 48 * 1024;
+constexpr u32 UNP_SM_SPAN = 64;                          // byte offsets inside dynamic shared memory
+constexpr u32 UNP_SM_STAGE = (UNP_SM_SPAN + UNP_SPAN_PADDED * 4 + 127) / 128 * 128;
+constexpr u32 UNP_SMEM_BYTES = UNP_SM_STAGE + UNP_STAGE_BYTES + 32;
+
+struct SmemBits {                                        // sequential reader over the padded span
+    const u32* sp;
+    u64 acc;
+    u32 nb, wi;
+    TRPX_DEVICE void init(const u32* sp_, u32 bit)
+    {
+        sp = sp_; wi = bit >> 5;
+        acc = (u64)sp[wi + (wi >> 4)] >> (bit & 31);
+        nb = 32 - (bit & 31);
+        ++wi;
+    }
+    TRPX_DEVICE void fill()                              // afterwards nb >= 32
+    {
+        if (nb < 32) { acc |= (u64)sp[wi + (wi >> 4)] << nb; nb += 32; ++wi; }
+    }
+    TRPX_DEVICE void skip(u32 n) { acc >>= n; nb -= n; } // n <= nb
+    TRPX_DEVICE u32 get(u32 n)                           // n in [0, 32]
+    {
+        fill();
+        const u32 v = n == 32 ? (u32)acc : (u32)acc & ((1u << n) - 1);
+        skip(n);
+        return v;
+    }
+    TRPX_DEVICE u64 get_wide(u32 s)                      // s in [1, 73]; returns the low 64 bits
+    {
+        u64 v = get(s < 32 ? s : 32);
+        if (s > 32) v |= (u64)get(s - 32 < 32 ? s - 32 : 32) << 32;
+        if (s > 64) (void)get(s - 64);
+        return v;
+    }
+};
+
+template <typename O> struct UnpCap { static constexpr u32 BLOCKS = UNP_STAGE_BYTES / (12 * sizeof(O)); };
+
+// One full block (12 values, width s >= 1) -> dst (aligned for the vector stores used below).
+template <typename O, bool SGN>
+TRPX_DEVICE void unpack_block12(SmemBits& br, u32 s, O* dst)
+{
+    constexpr u32 SO = sizeof(O);
+    if (SO == 2 && s <= 16) {
+        // two fields of s bits -> two 16-bit lanes with one multiply-add (the encoder's trick reversed)
+        const u32 m2 = s == 16 ? 0xffffffffu : (1u << (2 * s)) - 1;
+        const u32 K = 65536u - (1u << s);
+        const u32 KS = (0xffffu << s) & 0xffffu;          // sign extension of a 16-bit lane
+        u32 o[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            br.fill();
+            const u32 pm = (u32)br.acc & m2;
+            br.skip(2 * s);
+            u32 x = pm + (pm >> s) * K;
+            if (SGN) x |= ((x >> (s - 1)) & 0x00010001u) * KS;
+            o[i] = x;
+        }
+        uint2* d = (uint2*)dst;
+        d[0] = make_uint2(o[0], o[1]); d[1] = make_uint2(o[2], o[3]); d[2] = make_uint2(o[4], o[5]);
+        return;
+    }
+    if (SO == 1 && s <= 8) {
+        const u32 m4 = s == 8 ? 0xffffffffu : (1u << (4 * s)) - 1;
+        const u32 m2 = (1u << (2 * s)) - 1;
+        const u32 K8 = 256u - (1u << s);
+        const u32 KS = (0xffu << s) & 0xffu;
+        u32* d = (u32*)dst;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            br.fill();
+            const u32 q = (u32)br.acc & m4;
+            br.skip(4 * s);
+            const u32 p0 = q & m2, p1 = s == 8 ? (q >> 16) : (q >> (2 * s));
+            u32 x = (p0 + (p0 >> s) * K8) | ((p1 + (p1 >> s) * K8) << 16);
+            if (SGN) x |= ((x >> (s - 1)) & 0x01010101u) * KS;
+            d[i] = x;
+        }
+        return;
+    }
+    if (SO == 4 && s <= 32) {
+        u32 o[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            u32 v = br.get(s);
+            if (SGN && s < 32 && ((v >> (s - 1)) & 1)) v |= ~0u << s;
+            o[i] = v;
+        }
+        uint4* d = (uint4*)dst;
+        d[0] = make_uint4(o[0], o[1], o[2], o[3]); d[1] = make_uint4(o[4], o[5], o[6], o[7]); d[2] = make_uint4(o[8], o[9], o[10], o[11]);
+        return;
+    }
+    for (u32 i = 0; i < 12; ++i) dst[i] = convert_value<O, SGN>(s <= 32 ? (u64)br.get(s) : br.get_wide(s), s);
+}
+
+template <typename O, bool SGN>
+TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 1) prolix_unpack_seg_kernel(DecParams p)
+{
+    constexpr u32 SO = sizeof(O);
+    constexpr u32 CB = UnpCap<O>::BLOCKS;
+    TRPX_DYN_SMEM(sm);
+    u32* span = (u32*)(sm + UNP_SM_SPAN);
+    unsigned char* stage = sm + UNP_SM_STAGE;
+    const u32 t = tid();
+    const u32 parts = (p.subs_per_seg + UNP_NT - 1) / UNP_NT;       // CTAs per segment
+    const u64 j = bid() / parts;
+    const u32 h = bid() % parts;
+    if (j >= p.seg_base[p.n_frames]) return;
+    const SegInfo g = seg_info(p, j);
+    const u64 b0 = p.seg_b0[j];
+    const u32 m = h * UNP_NT + t;                                    // my sub-segment
+    const u64* row = p.ckpt + j * p.subs_per_seg;
+    // headers of this CTA: [kA, kB) in segment-local numbering, clipped at the frame's last block
+    const u32 seg_cnt = p.seg_count[j];
+    const u32 kA = h * UNP_NT < p.subs_per_seg ? ckpt_n(row[h * UNP_NT]) : seg_cnt;
+    u32 kB = (h + 1) * UNP_NT < p.subs_per_seg ? ckpt_n(row[(h + 1) * UNP_NT]) : seg_cnt;
+    if (b0 >= p.nblocks) return;
+    if ((u64)kB > p.nblocks - b0) kB = (u32)(p.nblocks - b0);
+    if (kA >= kB) return;                                            // uniform: nothing starts in this slice
+
+    // ---- stage the slice of the stream: 16-byte loads, 17-word pitch
+    const u64 slice_bit = g.base_bit + g.r0 + (u64)h * UNP_NT * SUB_BITS;   // absolute bit of the slice's start (multiple of 8)
+    const u64 a0 = (slice_bit >> 3) & ~15ull;                        // 16-byte aligned byte offset in the payload
+    {
+        const u64 safe_end = p.payload_bytes & ~15ull;
+        const u64 n_words = (p.payload_bytes + 3) >> 2;
+        const unsigned char* base = (const unsigned char*)p.payload;
+        for (u32 c = t; c < UNP_SPAN_WORDS / 4; c += UNP_NT) {
+            const u64 b = a0 + 16ull * c;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (b + 16 <= safe_end) {
+                v = *(const uint4*)(base + b);
+            } else if (b < p.payload_bytes) {
+                const u64 wi = b >> 2;
+                v.x = wi < n_words ? p.payload[wi] : 0u;
+                v.y = wi + 1 < n_words ? p.payload[wi + 1] : 0u;
+                v.z = wi + 2 < n_words ? p.payload[wi + 2] : 0u;
+                v.w = wi + 3 < n_words ? p.payload[wi + 3] : 0u;
+            }
+            const u32 i = 4 * c, pi = i + (i >> 4);                 // 4 consecutive words never straddle a pad
+            span[pi] = v.x; span[pi + 1] = v.y; span[pi + 2] = v.z; span[pi + 3] = v.w;
+        }
+    }
+
+    // ---- my headers: [k, k_end), first one at `rel` bits from the segment's start
+    u32 k = 0, k_end = 0, s = 0;
+    SmemBits br;
+    br.sp = span; br.acc = 0; br.nb = 0; br.wi = 0;
+    sync_block();
+    if (m < p.subs_per_seg) {
+        const u64 c0 = row[m];
+        k = ckpt_n(c0);
+        k_end = m + 1 < p.subs_per_seg ? ckpt_n(row[m + 1]) : seg_cnt;
+        if (k_end > kB) k_end = kB;
+        s = ckpt_s(c0);
+        if (k < k_end) br.init(span, (u32)(g.base_bit + g.r0 + ckpt_rel(c0) - a0 * 8));
+    }
+    O* outf = (O*)p.out + g.frame * p.n_values;
+    for (u32 c0 = kA; c0 < kB; c0 += CB) {
+        const u32 c1 = c0 + CB < kB ? c0 + CB : kB;
+        // the chunk's first value in global memory; the stage mirrors its 16-byte phase
+        const u64 v0 = (b0 + c0) * 12;
+        unsigned char* gdst = (unsigned char*)(outf + v0);
+        const u32 phase = (u32)((uintptr_t)gdst & 15);
+        unsigned char* sbase = stage + phase;
+        while (k < k_end && k < c1) {
+            const u64 b = b0 + k;
+            br.fill();
+            br.skip(decode_header(br.acc, s));
+            O* dst = (O*)(sbase + (size_t)(k - c0) * 12 * SO);
+            const u32 cnt = b + 1 == p.nblocks ? p.last_cnt : 12u;
+            if (s > 73) { atomic_max(p.status, DEC_MALFORMED); k = k_end; break; }
+            if (s == 0) {
+                for (u32 i = 0; i < cnt; ++i) dst[i] = (O)0;
+            } else if (cnt == 12) {
+                unpack_block12<O, SGN>(br, s, dst);
+            } else {
+                for (u32 i = 0; i < cnt; ++i) dst[i] = convert_value<O, SGN>(s <= 32 ? (u64)br.get(s) : br.get_wide(s), s);
+            }
+            ++k;
+            if (k == k_end && a0 * 8 + (u64)br.wi * 32 - br.nb > g.base_bit + g.frame_bits)
+                atomic_max(p.status, DEC_MALFORMED);                  // the last block runs past the frame's end
+        }
+        fence_async_smem();
+        sync_block();
+        // ---- store [v0, v1): unaligned head and tail bytes by hand, the 16-byte aligned middle as one bulk copy
+        const u64 v1 = (b0 + c1) * 12 < p.n_values ? (b0 + c1) * 12 : p.n_values;
+        const u32 bytes = (u32)((v1 - v0) * SO);
+        u32 head = (16 - phase) & 15;
+        if (head > bytes) head = bytes;
+        const u32 mid = (bytes - head) & ~15u;
+        for (u32 i = t; i < head; i += UNP_NT) gdst[i] = sbase[i];
+        for (u32 i = head + mid + t; i < bytes; i += UNP_NT) gdst[i] = sbase[i];
+        if (t == 0 && mid) {
+            bulk_s2g(gdst + head, sbase + head, mid);
+            bulk_commit();
+            bulk_wait_read0();
+        }
+        sync_block();
     }
 }
 

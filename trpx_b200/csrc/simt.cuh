@@ -202,6 +202,8 @@ inline cudaError_t launch_coop(void (*kern)(P), u32 grid, u32 block, size_t smem
 
 using ::emu::uint4;
 using ::emu::make_uint4;
+using ::emu::uint2;
+using ::emu::make_uint2;
 
 inline u32 tid() { return ::emu::cur().tid; }
 inline u32 bid() { return ::emu::cur().bid; }
