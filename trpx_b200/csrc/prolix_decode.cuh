@@ -83,6 +83,18 @@ TRPX_DEVICE u32 decode_header(u64 win, u32& s)
     return 12;
 }
 
+// The same, without data-dependent branches: (length, width after the header) for carried width s.
+TRPX_DEVICE void decode_header_bf(u32 win, u32 s, u32& hl, u32& s_new)
+{
+    const u32 s3 = (win >> 1) & 7, e2 = (win >> 4) & 3, e6 = (win >> 6) & 63;
+    const bool p7 = s3 == 7, p10 = p7 && e2 == 3;
+    const u32 sx = p10 ? 10 + e6 : s3 + (p7 ? e2 : 0u);
+    const u32 hx = p10 ? 12u : (p7 ? 6u : 4u);
+    const bool same = (win & 1) != 0;
+    hl = same ? 1u : hx;
+    s_new = same ? s : sx;
+}
+
 TRPX_HD u64 pack_state(u64 pos, u32 s) { return (pos << 8) | (u64)s; }
 TRPX_HD u64 state_pos(u64 st) { return st >> 8; }
 TRPX_HD u32 state_s(u64 st) { return (u32)(st & 0xff); }
@@ -123,26 +135,34 @@ TRPX_HD u32 ckpt_n(u64 c) { return (u32)c; }
 struct CkptSink {
     u64* row;               // this segment's checkpoints (nullptr: record nothing)
     u32 subs, next_m;
-    TRPX_DEVICE void init(u64* row_, u32 subs_) { row = row_; subs = subs_; next_m = 0; }
+    u32 next_rel;           // a header at rel >= next_rel opens a new sub-segment (0xffffffff: never)
+    TRPX_DEVICE void init(u64* row_, u32 subs_)
+    {
+        row = row_; subs = subs_; next_m = 0;
+        next_rel = row && subs ? 0u : 0xffffffffu;
+    }
     TRPX_DEVICE void at(u32 rel, u32 s_prev, u32 n)          // a header starts at rel
     {
-        if (!row) return;
+        if (rel < next_rel) return;                          // the common case: one compare
         const u32 m = rel >> SUB_SHIFT;
         while (next_m <= m && next_m < subs) row[next_m++] = pack_ckpt(rel, s_prev, n);
+        next_rel = next_m < subs ? next_m << SUB_SHIFT : 0xffffffffu;
     }
     TRPX_DEVICE void run(u32 rel, u32 n, u32 len)            // len one-bit headers (width 0) from rel
     {
-        if (!row) return;
+        if (rel + len <= next_rel) return;
         at(rel, 0, n);
         while (next_m < subs && (next_m << SUB_SHIFT) < rel + len) {   // boundaries inside the run are headers themselves
             const u32 r2 = next_m << SUB_SHIFT;
             row[next_m++] = pack_ckpt(r2, 0, n + (r2 - rel));
         }
+        next_rel = next_m < subs ? next_m << SUB_SHIFT : 0xffffffffu;
     }
     TRPX_DEVICE void finish(u32 rel_exit, u32 s_exit, u32 n)  // sub-segments in which no header starts any more
     {
         if (!row) return;
         while (next_m < subs) row[next_m++] = pack_ckpt(rel_exit, s_exit, n);
+        next_rel = 0xffffffffu;
     }
 };
 
@@ -201,7 +221,7 @@ struct WalkLane {
     u32 qA, qB;         // the first header at or after qA is the segment's entry; stop at the first one >= qB
     bool entered;
     u32 q_entry, s_entry;
-    u64 n;              // headers counted since the entry
+    u32 n;              // headers counted since the entry (a segment holds < 2^23 bits)
 };
 
 TRPX_DEVICE void walk_fetch(const DecParams& p, const WalkLane& L, u32 round, uint4 (&pre)[8])
@@ -259,27 +279,31 @@ TRPX_DEVICE void warp_walk(const DecParams& p, u32* buf, WalkLane& L, Sink& sink
         if (r + 1 < r_end) walk_fetch(p, L, r + 1, pre);    // in flight while this round is walked
         const u32 w0 = r * WALK_ROUND_STRIDE;
         for (;;) {
-            const u32 wl = (L.q >> 5) - w0;                 // (wraps for lanes that are ahead of this round)
-            const bool active = L.have && L.q < L.qB && wl <= 30u;
+            bool active = L.have && L.q < L.qB && (L.q >> 5) - w0 <= 30u;   // (wraps for lanes ahead of this round)
             if (!any_lane(active)) break;
-            if (active) {
-                if (!L.entered && L.q >= L.qA) { L.entered = true; L.q_entry = L.q; L.s_entry = L.s; L.n = 0; }
-                const u32 stop = L.entered ? L.qB : L.qA;
-                const u32 lo = buf[wl * WALK_PITCH + lane], hi = buf[(wl + 1) * WALK_PITCH + lane];
-                const u32 win = funnel_r(lo, hi, L.q & 31);
-                if (L.s == 0 && (win & 1)) {                 // run of '1' headers of empty blocks: 1 bit each
+#pragma unroll
+            for (int rep = 0; rep < 2; ++rep) {             // two steps per vote
+                if (rep) active = L.have && L.q < L.qB && (L.q >> 5) - w0 <= 30u;
+                if (active) {
+                    if (!L.entered && L.q >= L.qA) { L.entered = true; L.q_entry = L.q; L.s_entry = L.s; L.n = 0; }
+                    const u32 stop = L.entered ? L.qB : L.qA;
+                    const u32 wl = (L.q >> 5) - w0;
+                    const u32 lo = buf[wl * WALK_PITCH + lane], hi = buf[(wl + 1) * WALK_PITCH + lane];
+                    const u32 win = funnel_r(lo, hi, L.q & 31);
+                    // a run of '1' headers of empty blocks (1 bit each) is taken in one step
                     u32 run = (u32)ffs32(~win) - 1;          // ffs32(0) == 0 -> 0xffffffff: all 32 bits set
-                    if (run > 32u) run = 32u;
-                    if (run > stop - L.q) run = stop - L.q;
-                    if (L.entered) { sink.zeros(L.n, L.q, run); ck.run(L.q - L.qA, (u32)L.n, run); }
-                    L.n += run;
-                    L.q += run;
-                } else {
-                    if (L.entered) ck.at(L.q - L.qA, L.s, (u32)L.n);
-                    const u32 hl = decode_header((u64)win, L.s);
-                    if (L.entered) sink.block(L.n, L.q, L.s);
-                    L.q += hl + L.s * p.block;
-                    L.n += 1;
+                    run = run > 32u ? 32u : run;
+                    run = run > stop - L.q ? stop - L.q : run;
+                    const bool isrun = L.s == 0 && (win & 1);
+                    u32 hl, s_new;
+                    decode_header_bf(win, L.s, hl, s_new);
+                    if (L.entered) {
+                        if (isrun) { sink.zeros(L.n, L.q, run); ck.run(L.q - L.qA, (u32)L.n, run); }
+                        else { ck.at(L.q - L.qA, L.s, (u32)L.n); sink.block(L.n, L.q, s_new); }
+                    }
+                    L.q += isrun ? run : hl + s_new * p.block;
+                    L.n += isrun ? run : 1u;
+                    L.s = s_new;
                 }
             }
         }
@@ -381,7 +405,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_walk_kernel(DecParams p)
         ck.finish(L.q - L.qA, L.s, (u32)L.n);
         p.seg_entry[j] = pack_state(L.q_entry + delta, L.s_entry);
         p.seg_exit[j] = pack_state(L.q + delta, L.s);
-        p.seg_count[j] = L.n > 0xffffffffull ? 0xffffffffu : (u32)L.n;
+        p.seg_count[j] = L.n;
     }
 }
 
@@ -756,11 +780,20 @@ struct SmemBits {                                        // sequential reader ov
     }
 };
 
+// 32 stream bits starting at bit `pos` of the padded span (two neighbouring words, one funnel shift)
+TRPX_DEVICE u32 span_bits(const u32* sp, u32 pos)
+{
+    const u32 wi = pos >> 5, pi = wi + (wi >> 4);
+    return funnel_r(sp[pi], sp[pi + 1], pos & 31);
+}
+
 template <typename O> struct UnpCap { static constexpr u32 BLOCKS = UNP_STAGE_BYTES / (12 * sizeof(O)); };
 
-// One full block (12 values, width s >= 1) -> dst (aligned for the vector stores used below).
+// One full block (12 values of width s >= 1 starting at bit `pos`) -> dst (aligned for the vector
+// stores used below).  Every field group is fetched straight from its own bit position: twelve
+// independent extractions, no serial bit-reader state.
 template <typename O, bool SGN>
-TRPX_DEVICE void unpack_block12(SmemBits& br, u32 s, O* dst)
+TRPX_DEVICE void unpack_block12(const u32* sp, u32 pos, u32 s, O* dst)
 {
     constexpr u32 SO = sizeof(O);
     if (SO == 2 && s <= 16) {
@@ -771,9 +804,7 @@ TRPX_DEVICE void unpack_block12(SmemBits& br, u32 s, O* dst)
         u32 o[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-            br.fill();
-            const u32 pm = (u32)br.acc & m2;
-            br.skip(2 * s);
+            const u32 pm = span_bits(sp, pos + 2 * s * i) & m2;
             u32 x = pm + (pm >> s) * K;
             if (SGN) x |= ((x >> (s - 1)) & 0x00010001u) * KS;
             o[i] = x;
@@ -790,9 +821,7 @@ TRPX_DEVICE void unpack_block12(SmemBits& br, u32 s, O* dst)
         u32* d = (u32*)dst;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            br.fill();
-            const u32 q = (u32)br.acc & m4;
-            br.skip(4 * s);
+            const u32 q = span_bits(sp, pos + 4 * s * i) & m4;
             const u32 p0 = q & m2, p1 = s == 8 ? (q >> 16) : (q >> (2 * s));
             u32 x = (p0 + (p0 >> s) * K8) | ((p1 + (p1 >> s) * K8) << 16);
             if (SGN) x |= ((x >> (s - 1)) & 0x01010101u) * KS;
@@ -801,10 +830,11 @@ TRPX_DEVICE void unpack_block12(SmemBits& br, u32 s, O* dst)
         return;
     }
     if (SO == 4 && s <= 32) {
+        const u32 m = s == 32 ? 0xffffffffu : (1u << s) - 1;
         u32 o[12];
 #pragma unroll
         for (int i = 0; i < 12; ++i) {
-            u32 v = br.get(s);
+            u32 v = span_bits(sp, pos + s * i) & m;
             if (SGN && s < 32 && ((v >> (s - 1)) & 1)) v |= ~0u << s;
             o[i] = v;
         }
@@ -812,6 +842,8 @@ TRPX_DEVICE void unpack_block12(SmemBits& br, u32 s, O* dst)
         d[0] = make_uint4(o[0], o[1], o[2], o[3]); d[1] = make_uint4(o[4], o[5], o[6], o[7]); d[2] = make_uint4(o[8], o[9], o[10], o[11]);
         return;
     }
+    SmemBits br;
+    br.init(sp, pos);
     for (u32 i = 0; i < 12; ++i) dst[i] = convert_value<O, SGN>(s <= 32 ? (u64)br.get(s) : br.get_wide(s), s);
 }
 
@@ -861,13 +893,12 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 1) prolix_unpack_seg_kernel(DecParam
             }
             const u32 i = 4 * c, pi = i + (i >> 4);                 // 4 consecutive words never straddle a pad
             span[pi] = v.x; span[pi + 1] = v.y; span[pi + 2] = v.z; span[pi + 3] = v.w;
+            if ((i & 15) == 0 && i) span[pi - 1] = v.x;             // the pad repeats the word after it: word i+1 is always at +1
         }
     }
 
-    // ---- my headers: [k, k_end), first one at `rel` bits from the segment's start
-    u32 k = 0, k_end = 0, s = 0;
-    SmemBits br;
-    br.sp = span; br.acc = 0; br.nb = 0; br.wi = 0;
+    // ---- my headers: [k, k_end), the first one at bit `pos` of the span
+    u32 k = 0, k_end = 0, s = 0, pos = 0;
     sync_block();
     if (m < p.subs_per_seg) {
         const u64 c0 = row[m];
@@ -875,8 +906,9 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 1) prolix_unpack_seg_kernel(DecParam
         k_end = m + 1 < p.subs_per_seg ? ckpt_n(row[m + 1]) : seg_cnt;
         if (k_end > kB) k_end = kB;
         s = ckpt_s(c0);
-        if (k < k_end) br.init(span, (u32)(g.base_bit + g.r0 + ckpt_rel(c0) - a0 * 8));
+        pos = (u32)(g.base_bit + g.r0 + ckpt_rel(c0) - a0 * 8);
     }
+    const u32 frame_end_pos = (u32)((g.base_bit + g.frame_bits - a0 * 8 < 0xffffffffull) ? g.base_bit + g.frame_bits - a0 * 8 : 0xffffffffull);
     O* outf = (O*)p.out + g.frame * p.n_values;
     for (u32 c0 = kA; c0 < kB; c0 += CB) {
         const u32 c1 = c0 + CB < kB ? c0 + CB : kB;
@@ -886,22 +918,24 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 1) prolix_unpack_seg_kernel(DecParam
         const u32 phase = (u32)((uintptr_t)gdst & 15);
         unsigned char* sbase = stage + phase;
         while (k < k_end && k < c1) {
-            const u64 b = b0 + k;
-            br.fill();
-            br.skip(decode_header(br.acc, s));
+            u32 hl;
+            decode_header_bf(span_bits(span, pos), s, hl, s);
+            pos += hl;
             O* dst = (O*)(sbase + (size_t)(k - c0) * 12 * SO);
-            const u32 cnt = b + 1 == p.nblocks ? p.last_cnt : 12u;
+            const u32 cnt = b0 + k + 1 == p.nblocks ? p.last_cnt : 12u;
             if (s > 73) { atomic_max(p.status, DEC_MALFORMED); k = k_end; break; }
             if (s == 0) {
                 for (u32 i = 0; i < cnt; ++i) dst[i] = (O)0;
             } else if (cnt == 12) {
-                unpack_block12<O, SGN>(br, s, dst);
+                unpack_block12<O, SGN>(span, pos, s, dst);
             } else {
+                SmemBits br;
+                br.init(span, pos);
                 for (u32 i = 0; i < cnt; ++i) dst[i] = convert_value<O, SGN>(s <= 32 ? (u64)br.get(s) : br.get_wide(s), s);
             }
+            pos += s * cnt;
             ++k;
-            if (k == k_end && a0 * 8 + (u64)br.wi * 32 - br.nb > g.base_bit + g.frame_bits)
-                atomic_max(p.status, DEC_MALFORMED);                  // the last block runs past the frame's end
+            if (k == k_end && pos > frame_end_pos) atomic_max(p.status, DEC_MALFORMED);   // the last block runs past the frame's end
         }
         fence_async_smem();
         sync_block();
