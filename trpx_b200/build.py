@@ -42,5 +42,30 @@ def build(force=False, verbose=False):
     return OUT
 
 
+ROOT = os.path.dirname(HERE)
+HOST_TARGETS = {"terse_selftest": [os.path.join(ROOT, "cxx", "terse_selftest.cpp")]}
+
+
+def build_host(force=False):
+    """Host-side C++ on top of the C ABI (include/trpx/Terse.hpp): g++ -std=c++20, linked against the in-tree .so."""
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    outs = []
+    for name, srcs in HOST_TARGETS.items():
+        srcs = [s for s in srcs if os.path.exists(s)]
+        if not srcs:
+            continue
+        out = os.path.join(ROOT, "cxx", name)
+        deps = srcs + [os.path.join(ROOT, "include", "trpx", "Terse.hpp"), os.path.join(ROOT, "include", "trpx_b200.h"), OUT]
+        if force or not os.path.exists(out) or any(os.path.getmtime(out) < os.path.getmtime(d) for d in deps if os.path.exists(d)):
+            cmd = [cxx, "-std=c++20", "-O2", "-DNDEBUG", "-Wall", "-I", os.path.join(ROOT, "include")] + srcs + [
+                "-L", HERE, "-ltrpx_b200", "-Wl,-rpath," + HERE, "-o", out]
+            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout)
+                raise RuntimeError("g++ failed building " + name)
+        outs.append(out)
+    return outs
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

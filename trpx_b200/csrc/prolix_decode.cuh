@@ -918,6 +918,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 1) prolix_unpack_seg_kernel(DecParam
         const u32 phase = (u32)((uintptr_t)gdst & 15);
         unsigned char* sbase = stage + phase;
         while (k < k_end && k < c1) {
+            if (pos >= (UNP_NT * SUB_BYTES + 16) * 8) { atomic_max(p.status, DEC_MALFORMED); k = k_end; break; }   // never read past the tail
             u32 hl;
             decode_header_bf(span_bits(span, pos), s, hl, s);
             pos += hl;

@@ -424,7 +424,8 @@ TRPX_DEVICE u32 tail_handoff(const EncParams& p, u64 tile, const u32* stg, u32 t
     const u32 sh = (u32)(P0 & 31);
     // Our bits of the word the NEXT tile starts in.  When we own a complete word (k >= 1) they do not
     // depend on our predecessor: publish before waiting, so the hand-off never chains across tiles.
-    tout = window_word(stg, nstg, k, sh);
+    // (only bits below Pn belong to us; a frame end may leave Pn up to 8 bits past the staged data)
+    tout = window_word(stg, nstg, k, sh) & ((1u << (Pn & 31)) - 1);
     if (k >= 1) st_relaxed(&p.tails[tile], TAIL_VALID | (u64)tout);
     u64 tin = 0;
     if (sh != 0) {                                         // the word we start in is ours to store
