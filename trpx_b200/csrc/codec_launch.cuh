@@ -316,7 +316,7 @@ inline void decode_async(Launcher& L, const void* d_payload, u64 payload_bytes, 
     L.count("prolix_segments");
     if (L.err != cudaSuccess) return;
     const u32 walk_grid = (u32)div_up(pl.max_segs, WALK_NT);
-    const size_t walk_smem = (size_t)(WALK_NT / 32) * WALK_BUF_WORDS * 4;
+    const size_t walk_smem = HDR_TAB_BYTES + (size_t)(WALK_NT / 32) * WALK_BUF_WORDS * 4;
     L.err = launch(prolix_walk_kernel<WALK_NT>, walk_grid, (u32)WALK_NT, walk_smem, L.stream, p);
     L.count("prolix_walk");
     if (L.err != cudaSuccess) return;

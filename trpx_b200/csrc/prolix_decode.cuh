@@ -95,6 +95,25 @@ TRPX_DEVICE void decode_header_bf(u32 win, u32 s, u32& hl, u32& s_new)
     s_new = same ? s : sx;
 }
 
+// Header look-up table in shared memory: 12 stream bits -> length | "same width" flag | new width.
+constexpr u32 HDR_TAB_ENTRIES = 4096, HDR_TAB_BYTES = HDR_TAB_ENTRIES * 2;
+constexpr u32 HDR_SAME = 0x80;
+template <int NT>
+TRPX_DEVICE void build_header_table(unsigned short* tab)      // caller syncs afterwards
+{
+    for (u32 i = tid(); i < HDR_TAB_ENTRIES; i += NT) {
+        u32 hl, sx;
+        decode_header_bf(i & ~1u, 0, hl, sx);                  // the explicit reading of these 12 bits
+        tab[i] = (unsigned short)((i & 1) ? (1u | HDR_SAME) : (hl | (sx << 8)));
+    }
+}
+TRPX_DEVICE void lookup_header(const unsigned short* tab, u32 win, u32 s, u32& hl, u32& s_new)
+{
+    const u32 e = tab[win & (HDR_TAB_ENTRIES - 1)];
+    hl = e & 15;
+    s_new = (e & HDR_SAME) ? s : e >> 8;
+}
+
 TRPX_HD u64 pack_state(u64 pos, u32 s) { return (pos << 8) | (u64)s; }
 TRPX_HD u64 state_pos(u64 st) { return st >> 8; }
 TRPX_HD u32 state_s(u64 st) { return (u32)(st & 0xff); }
@@ -122,9 +141,10 @@ struct StreamWindow {
     }
 };
 
-// Checkpoint of a 64-byte sub-segment: the first header at or after its first bit, as
+// Checkpoint of a 32-byte sub-segment: the first header at or after its first bit, as
 // (bit offset from the segment's start : 24 | width carried into that header : 8 | headers of the segment before it : 32).
-constexpr u32 SUB_BYTES = 64, SUB_BITS = SUB_BYTES * 8, SUB_SHIFT = 9;
+constexpr u32 SUB_BYTES = 32, SUB_BITS = SUB_BYTES * 8, SUB_SHIFT = 8;
+constexpr u32 SUB_WORDS = SUB_BYTES / 4, SUB_WSHIFT = 3;   // span padding: one extra word per sub-segment
 TRPX_HD u64 pack_ckpt(u32 rel, u32 s, u32 n) { return ((u64)rel << 40) | ((u64)(s & 0xff) << 32) | (u64)n; }
 TRPX_HD u32 ckpt_rel(u64 c) { return (u32)(c >> 40); }
 TRPX_HD u32 ckpt_s(u64 c) { return (u32)(c >> 32) & 0xff; }
@@ -260,16 +280,22 @@ TRPX_DEVICE void walk_stage(u32* buf, const uint4 (&pre)[8])
 }
 
 // All 32 lanes of a warp call this together.  sink.block(k, q, s) / sink.zeros(k, q, run) see the k-th
-// header after the entry at lane-relative bit q.
+// header after the entry at lane-relative bit q.  The common step is short and branch-light: two LDS
+// + funnel shift for the window, one table look-up for the header, one compare for "anything
+// special here?" (entering the segment, a new checkpoint, a run of empty blocks).
 template <class Sink>
-TRPX_DEVICE void warp_walk(const DecParams& p, u32* buf, WalkLane& L, Sink& sink, CkptSink& ck)
+TRPX_DEVICE void warp_walk(const DecParams& p, u32* buf, const unsigned short* tab, WalkLane& L, Sink& sink, CkptSink& ck)
 {
     const u32 lane = tid() & 31;
+    if (!L.have) { L.qB = 0; L.q = 0xffffffffu; }
     const u32 my_rounds = L.have ? ((L.qB + 31) >> 5) / WALK_ROUND_STRIDE + 1 : 0u;
     const u32 first_round = L.have ? (L.q >> 5) / WALK_ROUND_STRIDE : 0xffffffffu;
     u32 r = warp_min_u32(first_round);
     const u32 r_end = warp_max(my_rounds);
     if (r >= r_end) return;
+    // next position at which the slow path has work: the segment's first bit, then every new checkpoint
+    u32 q_event = L.entered ? (ck.next_rel == 0xffffffffu ? 0xffffffffu : L.qA + ck.next_rel) : L.qA;
+    const u32 blk = p.block;
     uint4 pre[8];
     walk_fetch(p, L, r, pre);
     for (; r < r_end; ++r) {
@@ -278,31 +304,38 @@ TRPX_DEVICE void warp_walk(const DecParams& p, u32* buf, WalkLane& L, Sink& sink
         sync_warp();
         if (r + 1 < r_end) walk_fetch(p, L, r + 1, pre);    // in flight while this round is walked
         const u32 w0 = r * WALK_ROUND_STRIDE;
+        const u32 q_round = (w0 + 31) << 5;                 // headers below this bit are readable in this round
+        const u32 qlim = L.qB < q_round ? L.qB : q_round;   // (lanes ahead of this round have q >= q_round)
+        const u32* col = buf + lane - w0 * WALK_PITCH;
         for (;;) {
-            bool active = L.have && L.q < L.qB && (L.q >> 5) - w0 <= 30u;   // (wraps for lanes ahead of this round)
-            if (!any_lane(active)) break;
+            if (!any_lane(L.q < qlim)) break;
 #pragma unroll
             for (int rep = 0; rep < 2; ++rep) {             // two steps per vote
-                if (rep) active = L.have && L.q < L.qB && (L.q >> 5) - w0 <= 30u;
-                if (active) {
-                    if (!L.entered && L.q >= L.qA) { L.entered = true; L.q_entry = L.q; L.s_entry = L.s; L.n = 0; }
-                    const u32 stop = L.entered ? L.qB : L.qA;
-                    const u32 wl = (L.q >> 5) - w0;
-                    const u32 lo = buf[wl * WALK_PITCH + lane], hi = buf[(wl + 1) * WALK_PITCH + lane];
-                    const u32 win = funnel_r(lo, hi, L.q & 31);
-                    // a run of '1' headers of empty blocks (1 bit each) is taken in one step
-                    u32 run = (u32)ffs32(~win) - 1;          // ffs32(0) == 0 -> 0xffffffff: all 32 bits set
-                    run = run > 32u ? 32u : run;
-                    run = run > stop - L.q ? stop - L.q : run;
+                if (L.q < qlim) {
+                    const u32 wi = L.q >> 5;
+                    const u32 win = funnel_r(col[wi * WALK_PITCH], col[wi * WALK_PITCH + WALK_PITCH], L.q & 31);
                     const bool isrun = L.s == 0 && (win & 1);
-                    u32 hl, s_new;
-                    decode_header_bf(win, L.s, hl, s_new);
-                    if (L.entered) {
-                        if (isrun) { sink.zeros(L.n, L.q, run); ck.run(L.q - L.qA, (u32)L.n, run); }
-                        else { ck.at(L.q - L.qA, L.s, (u32)L.n); sink.block(L.n, L.q, s_new); }
+                    if (L.q >= q_event || isrun) {          // ---- slow path
+                        if (!L.entered && L.q >= L.qA) { L.entered = true; L.q_entry = L.q; L.s_entry = L.s; L.n = 0; }
+                        if (isrun) {                        // a run of '1' headers of empty blocks, 1 bit each
+                            const u32 stop = L.entered ? L.qB : L.qA;
+                            u32 run = (u32)ffs32(~win) - 1; // ffs32(0) == 0 -> 0xffffffff: all 32 bits set
+                            run = run > 32u ? 32u : run;
+                            run = run > stop - L.q ? stop - L.q : run;
+                            if (L.entered) { sink.zeros(L.n, L.q, run); ck.run(L.q - L.qA, L.n, run); }
+                            L.q += run;
+                            L.n += run;
+                        } else if (L.entered) {
+                            ck.at(L.q - L.qA, L.s, L.n);
+                        }
+                        q_event = L.entered ? (ck.next_rel == 0xffffffffu ? 0xffffffffu : L.qA + ck.next_rel) : L.qA;
+                        if (isrun) continue;
                     }
-                    L.q += isrun ? run : hl + s_new * p.block;
-                    L.n += isrun ? run : 1u;
+                    u32 hl, s_new;
+                    lookup_header(tab, win, L.s, hl, s_new);
+                    if (L.entered) sink.block(L.n, L.q, s_new);
+                    L.q += hl + s_new * blk;
+                    L.n += 1;
                     L.s = s_new;
                 }
             }
@@ -380,7 +413,10 @@ template <int NT>
 TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_walk_kernel(DecParams p)
 {
     TRPX_DYN_SMEM(sm);
-    u32* buf = (u32*)sm + (tid() >> 5) * WALK_BUF_WORDS;
+    unsigned short* tab = (unsigned short*)sm;
+    u32* buf = (u32*)(sm + HDR_TAB_BYTES) + (tid() >> 5) * WALK_BUF_WORDS;
+    build_header_table<NT>(tab);
+    sync_block();
     const u64 j = (u64)bid() * NT + tid();
     WalkLane L;
     L.have = j < p.seg_base[p.n_frames];
@@ -399,7 +435,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_walk_kernel(DecParams p)
     NoSink ns;
     CkptSink ck;
     ck.init(L.have && p.ckpt ? p.ckpt + j * p.subs_per_seg : nullptr, p.subs_per_seg);
-    warp_walk(p, buf, L, ns, ck);
+    warp_walk(p, buf, tab, L, ns, ck);
     if (L.have) {
         if (!L.entered) { L.q_entry = L.q; L.s_entry = L.s; L.n = 0; }   // the warm-up jumped over the whole segment
         ck.finish(L.q - L.qA, L.s, (u32)L.n);
@@ -539,7 +575,10 @@ template <int NT>
 TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_emit_kernel(DecParams p)
 {
     TRPX_DYN_SMEM(sm);
-    u32* buf = (u32*)sm + (tid() >> 5) * WALK_BUF_WORDS;
+    unsigned short* tab = (unsigned short*)sm;
+    u32* buf = (u32*)(sm + HDR_TAB_BYTES) + (tid() >> 5) * WALK_BUF_WORDS;
+    build_header_table<NT>(tab);
+    sync_block();
     const u64 j = (u64)bid() * NT + tid();
     WalkLane L;
     L.have = j < p.seg_base[p.n_frames];
@@ -565,7 +604,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_emit_kernel(DecParams p)
     }
     CkptSink ck;
     ck.init(nullptr, 0);
-    warp_walk(p, buf, L, sink, ck);
+    warp_walk(p, buf, tab, L, sink, ck);
     if (L.have) {
         sink.flush();
         if (sink.bad) atomic_max(p.status, DEC_MALFORMED);
@@ -733,18 +772,19 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(DEC_NT, 1) prolix_unpack_kernel(DecParams p)
     }
 }
 
-// ------------------------------------------------------------------ P2 (fast path): re-walk 64-byte sub-segments and unpack
+// ------------------------------------------------------------------ P2 (fast path): re-walk 32-byte sub-segments and unpack
 // One thread per sub-segment: from its exact checkpoint it reads headers and values with ONE
-// sequential bit reader over shared memory (the CTA's slice of the stream is staged there with a
-// 17-word pitch per 16 words, so that lanes 64 bytes apart hit different banks), and writes whole
+// sequential bit reader over shared memory (the CTA's slice of the stream is staged there with one
+// pad word per sub-segment, so that lanes 32 bytes apart hit different banks), and writes whole
 // blocks into an output stage in block order.  The stage leaves with one TMA bulk store.  No widths
 // array, no second header pass over global memory.
-constexpr int UNP_NT = 128;                              // sub-segments (threads) per CTA: 8 KB of stream
+constexpr int UNP_NT = 256;                              // sub-segments (threads) per CTA: 8 KB of stream
 constexpr u32 UNP_TAIL_WORDS = 64;                       // a block that starts in the slice ends inside this tail
 constexpr u32 UNP_SPAN_WORDS = UNP_NT * (SUB_BYTES / 4) + UNP_TAIL_WORDS + 4;
-constexpr u32 UNP_SPAN_PADDED = UNP_SPAN_WORDS + UNP_SPAN_WORDS / 16 + 4;
+constexpr u32 UNP_SPAN_PADDED = UNP_SPAN_WORDS + UNP_SPAN_WORDS / SUB_WORDS + 4;
 constexpr u32 UNP_STAGE_BYTES = 48 * 1024;
-constexpr u32 UNP_SM_SPAN = 64;                          // byte offsets inside dynamic shared memory
+constexpr u32 UNP_SM_TAB = 64;                           // byte offsets inside dynamic shared memory
+constexpr u32 UNP_SM_SPAN = UNP_SM_TAB + HDR_TAB_BYTES;
 constexpr u32 UNP_SM_STAGE = (UNP_SM_SPAN + UNP_SPAN_PADDED * 4 + 127) / 128 * 128;
 constexpr u32 UNP_SMEM_BYTES = UNP_SM_STAGE + UNP_STAGE_BYTES + 32;
 
@@ -755,13 +795,13 @@ struct SmemBits {                                        // sequential reader ov
     TRPX_DEVICE void init(const u32* sp_, u32 bit)
     {
         sp = sp_; wi = bit >> 5;
-        acc = (u64)sp[wi + (wi >> 4)] >> (bit & 31);
+        acc = (u64)sp[wi + (wi >> SUB_WSHIFT)] >> (bit & 31);
         nb = 32 - (bit & 31);
         ++wi;
     }
     TRPX_DEVICE void fill()                              // afterwards nb >= 32
     {
-        if (nb < 32) { acc |= (u64)sp[wi + (wi >> 4)] << nb; nb += 32; ++wi; }
+        if (nb < 32) { acc |= (u64)sp[wi + (wi >> SUB_WSHIFT)] << nb; nb += 32; ++wi; }
     }
     TRPX_DEVICE void skip(u32 n) { acc >>= n; nb -= n; } // n <= nb
     TRPX_DEVICE u32 get(u32 n)                           // n in [0, 32]
@@ -783,7 +823,7 @@ struct SmemBits {                                        // sequential reader ov
 // 32 stream bits starting at bit `pos` of the padded span (two neighbouring words, one funnel shift)
 TRPX_DEVICE u32 span_bits(const u32* sp, u32 pos)
 {
-    const u32 wi = pos >> 5, pi = wi + (wi >> 4);
+    const u32 wi = pos >> 5, pi = wi + (wi >> SUB_WSHIFT);
     return funnel_r(sp[pi], sp[pi + 1], pos & 31);
 }
 
@@ -853,6 +893,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 1) prolix_unpack_seg_kernel(DecParam
     constexpr u32 SO = sizeof(O);
     constexpr u32 CB = UnpCap<O>::BLOCKS;
     TRPX_DYN_SMEM(sm);
+    unsigned short* tab = (unsigned short*)(sm + UNP_SM_TAB);
     u32* span = (u32*)(sm + UNP_SM_SPAN);
     unsigned char* stage = sm + UNP_SM_STAGE;
     const u32 t = tid();
@@ -872,7 +913,8 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 1) prolix_unpack_seg_kernel(DecParam
     if ((u64)kB > p.nblocks - b0) kB = (u32)(p.nblocks - b0);
     if (kA >= kB) return;                                            // uniform: nothing starts in this slice
 
-    // ---- stage the slice of the stream: 16-byte loads, 17-word pitch
+    build_header_table<UNP_NT>(tab);
+    // ---- stage the slice of the stream: 16-byte loads, one pad word per sub-segment
     const u64 slice_bit = g.base_bit + g.r0 + (u64)h * UNP_NT * SUB_BITS;   // absolute bit of the slice's start (multiple of 8)
     const u64 a0 = (slice_bit >> 3) & ~15ull;                        // 16-byte aligned byte offset in the payload
     {
@@ -891,9 +933,9 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 1) prolix_unpack_seg_kernel(DecParam
                 v.z = wi + 2 < n_words ? p.payload[wi + 2] : 0u;
                 v.w = wi + 3 < n_words ? p.payload[wi + 3] : 0u;
             }
-            const u32 i = 4 * c, pi = i + (i >> 4);                 // 4 consecutive words never straddle a pad
+            const u32 i = 4 * c, pi = i + (i >> SUB_WSHIFT);        // 4 consecutive words never straddle a pad
             span[pi] = v.x; span[pi + 1] = v.y; span[pi + 2] = v.z; span[pi + 3] = v.w;
-            if ((i & 15) == 0 && i) span[pi - 1] = v.x;             // the pad repeats the word after it: word i+1 is always at +1
+            if ((i & (SUB_WORDS - 1)) == 0 && i) span[pi - 1] = v.x;   // the pad repeats the word after it: word i+1 is always at +1
         }
     }
 
@@ -920,7 +962,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 1) prolix_unpack_seg_kernel(DecParam
         while (k < k_end && k < c1) {
             if (pos >= (UNP_NT * SUB_BYTES + 16) * 8) { atomic_max(p.status, DEC_MALFORMED); k = k_end; break; }   // never read past the tail
             u32 hl;
-            decode_header_bf(span_bits(span, pos), s, hl, s);
+            lookup_header(tab, span_bits(span, pos), s, hl, s);
             pos += hl;
             O* dst = (O*)(sbase + (size_t)(k - c0) * 12 * SO);
             const u32 cnt = b0 + k + 1 == p.nblocks ? p.last_cnt : 12u;

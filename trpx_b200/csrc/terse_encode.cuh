@@ -278,7 +278,7 @@ TRPX_DEVICE void zero_boundary_words(u32* stg, u32 off, u32 tile_bits)
 {
     const u32 t = tid();
     if ((t & 31) == 0) stg[off >> 5] = 0;
-    if (t == NT - 1) { stg[tile_bits >> 5] = 0; stg[(tile_bits >> 5) + 1] = 0; }   // partial last word + zero padding
+    if (t == NT - 1) { stg[tile_bits >> 5] = 0; stg[(tile_bits >> 5) + 1] = 0; stg[(tile_bits >> 5) + 2] = 0; }   // partial last word + zero padding
 }
 
 // Resolve the partial words inside a warp without atomics.  OR of disjoint bit fields == ADD, so
@@ -515,7 +515,7 @@ struct EncGeom {
     // (bits / 32 + 1) words plus a zero word on either side (window_word), rounded to 4: ~0.7 K words
     // for a typical 512^2 u16 tile, WORST_WORDS when nothing compresses.  The ring always holds two
     // worst-case tiles; with typical data ENC_DEPTH tiles are in flight.
-    static constexpr int WORST_WORDS = ((TILE_BLOCKS * P::MAXBITS + 31) / 32 + 1 + 2 + 3) / 4 * 4;
+    static constexpr int WORST_WORDS = ((TILE_BLOCKS * P::MAXBITS + 31) / 32 + 1 + 3 + 3) / 4 * 4;
     static constexpr int RING_WORDS = 2 * WORST_WORDS > 9216 ? 2 * WORST_WORDS : 9216;
     static constexpr int SMEM_BYTES = SM_HEADER + ENC_STAGES * STAGE_BYTES + RING_WORDS * 4;
     static constexpr int THREADS = NT + 32 * ENC_RESOLVERS;   // worker warps + resolver warps
@@ -716,7 +716,8 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_RESOLVERS, 3) terse_encode_ker
         if (t == 0) st_relaxed(&p.tdesc[tile], TD_VALID | (u64)tile_bits);
 
         // ---- room in the ring: physically contiguous, one zero word in front (window_word reads stg[-1])
-        const u32 need = ((tile_bits >> 5) + 1 + 2 + 3) & ~3u;
+        // words -1 .. (bits/32)+2: a frame end may push the window one word past the zero pad (tail_handoff)
+        const u32 need = ((tile_bits >> 5) + 1 + 3 + 3) & ~3u;
         u32 vbase = vhead;
         if (vbase % ring_words + need > ring_words) vbase += ring_words - vbase % ring_words;
         bool stored = false;
