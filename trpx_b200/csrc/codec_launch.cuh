@@ -182,7 +182,7 @@ struct DecPlan {
     bool staged;                  // block == 12 and 16-byte aligned frames: fused re-walk + unpack kernel (TMA store)
     u64 nblocks, tiles_per_frame, n_tiles, max_segs;
     u32 last_cnt, seg_bytes, warm_bytes, subs_per_seg;
-    size_t smem_unpack, off_ckpt;
+    size_t smem_unpack, off_ckpt, off_hdr_tab, off_segd;
     // scratch layout (byte offsets)
     size_t off_frame_ends, off_seg_base, off_seg_frame, off_seg_entry, off_seg_exit, off_seg_count,
         off_seg_b0, off_changed, off_zero_begin, off_widths, off_anchors, scratch_bytes;
@@ -220,6 +220,8 @@ inline DecPlan dec_plan(int out_dtype, u64 payload_bytes, u64 n_values, u64 n_fr
     pl.off_seg_b0 = o;     o = align_up(o + pl.max_segs * 8, 256);
     pl.off_zero_begin = o;                                   // everything from here is zeroed per call
     pl.off_changed = o;    o = align_up(o + 16, 256);
+    pl.off_hdr_tab = o;    o = align_up(o + HDR_TAB_BYTES, 256);
+    pl.off_segd = o;       o = align_up(o + (pl.staged ? pl.max_segs * 32 : 0), 256);
     if (pl.staged) {                                         // fast path: checkpoints instead of widths + anchors
         pl.off_ckpt = o;   o = align_up(o + pl.max_segs * pl.subs_per_seg * 8, 256);
         pl.off_anchors = pl.off_widths = o;
@@ -291,6 +293,8 @@ inline void decode_async(Launcher& L, const void* d_payload, u64 payload_bytes, 
     p.anchors = (u64*)(sc + pl.off_anchors);
     p.ckpt = pl.staged ? (u64*)(sc + pl.off_ckpt) : nullptr;
     p.subs_per_seg = pl.subs_per_seg;
+    p.hdr_tab = (unsigned short*)(sc + pl.off_hdr_tab);
+    p.segd = pl.staged ? (u64*)(sc + pl.off_segd) : nullptr;
     p.tile_blocks = DEC_TB;
     p.tiles_per_frame = pl.tiles_per_frame;
     p.out = d_out;

@@ -50,6 +50,9 @@ struct DecParams {
     // P1 -> fused P2: exact checkpoints, one per SUB_BYTES of every segment (nullptr on the generic path)
     u64* ckpt;              // [max_segs * subs_per_seg]: first header at or after the sub-segment's first bit
     u32 subs_per_seg;
+    unsigned short* hdr_tab; // [4096] header look-up table in global memory (written by prolix_segments_kernel)
+    u64* segd;              // [max_segs * 4] per segment: absolute bit of its start, absolute bit of its frame's end,
+                            // index of its first block in the frame, frame | header count << 32 (written by the resolve kernel)
     // P1 -> P2
     unsigned char* widths;  // [n_frames * nblocks], zeroed
     u64* anchors;           // [n_frames * tiles_per_frame] frame-relative bit of each tile's first header
@@ -107,6 +110,13 @@ TRPX_DEVICE void build_header_table(unsigned short* tab)      // caller syncs af
         tab[i] = (unsigned short)((i & 1) ? (1u | HDR_SAME) : (hl | (sx << 8)));
     }
 }
+template <int NT>
+TRPX_DEVICE void copy_header_table(unsigned short* tab, const unsigned short* gtab)   // caller syncs afterwards
+{
+    const uint4* src = (const uint4*)gtab;
+    uint4* dst = (uint4*)tab;
+    for (u32 i = tid(); i < HDR_TAB_BYTES / 16; i += NT) dst[i] = src[i];
+}
 TRPX_DEVICE void lookup_header(const unsigned short* tab, u32 win, u32 s, u32& hl, u32& s_new)
 {
     const u32 e = tab[win & (HDR_TAB_ENTRIES - 1)];
@@ -144,7 +154,6 @@ struct StreamWindow {
 // Checkpoint of a 32-byte sub-segment: the first header at or after its first bit, as
 // (bit offset from the segment's start : 24 | width carried into that header : 8 | headers of the segment before it : 32).
 constexpr u32 SUB_BYTES = 32, SUB_BITS = SUB_BYTES * 8, SUB_SHIFT = 8;
-constexpr u32 SUB_WORDS = SUB_BYTES / 4, SUB_WSHIFT = 3;   // span padding: one extra word per sub-segment
 TRPX_HD u64 pack_ckpt(u32 rel, u32 s, u32 n) { return ((u64)rel << 40) | ((u64)(s & 0xff) << 32) | (u64)n; }
 TRPX_HD u32 ckpt_rel(u64 c) { return (u32)(c >> 40); }
 TRPX_HD u32 ckpt_s(u64 c) { return (u32)(c >> 32) & 0xff; }
@@ -166,6 +175,16 @@ struct CkptSink {
         if (rel < next_rel) return;                          // the common case: one compare
         const u32 m = rel >> SUB_SHIFT;
         while (next_m <= m && next_m < subs) row[next_m++] = pack_ckpt(rel, s_prev, n);
+        next_rel = next_m < subs ? next_m << SUB_SHIFT : 0xffffffffu;
+    }
+    // The same for the walkers' hot loop, without a divergent branch in the common case (a header opens at
+    // most ONE new sub-segment): a predicated 8-byte store and two selects.
+    TRPX_DEVICE void at_fast(u32 rel, u32 s_prev, u32 n)
+    {
+        if (rel < next_rel) return;
+        if ((rel >> SUB_SHIFT) != next_m) { at(rel, s_prev, n); return; }   // skipped sub-segments: rare
+        row[next_m] = pack_ckpt(rel, s_prev, n);
+        ++next_m;
         next_rel = next_m < subs ? next_m << SUB_SHIFT : 0xffffffffu;
     }
     TRPX_DEVICE void run(u32 rel, u32 n, u32 len)            // len one-bit headers (width 0) from rel
@@ -293,8 +312,8 @@ TRPX_DEVICE void warp_walk(const DecParams& p, u32* buf, const unsigned short* t
     u32 r = warp_min_u32(first_round);
     const u32 r_end = warp_max(my_rounds);
     if (r >= r_end) return;
-    // next position at which the slow path has work: the segment's first bit, then every new checkpoint
-    u32 q_event = L.entered ? (ck.next_rel == 0xffffffffu ? 0xffffffffu : L.qA + ck.next_rel) : L.qA;
+    // next position at which the slow path has work: the segment's first bit (afterwards only runs of empty blocks)
+    u32 q_event = L.entered ? 0xffffffffu : L.qA;
     const u32 blk = p.block;
     uint4 pre[8];
     walk_fetch(p, L, r, pre);
@@ -325,15 +344,13 @@ TRPX_DEVICE void warp_walk(const DecParams& p, u32* buf, const unsigned short* t
                             if (L.entered) { sink.zeros(L.n, L.q, run); ck.run(L.q - L.qA, L.n, run); }
                             L.q += run;
                             L.n += run;
-                        } else if (L.entered) {
-                            ck.at(L.q - L.qA, L.s, L.n);
                         }
-                        q_event = L.entered ? (ck.next_rel == 0xffffffffu ? 0xffffffffu : L.qA + ck.next_rel) : L.qA;
+                        q_event = L.entered ? 0xffffffffu : L.qA;
                         if (isrun) continue;
                     }
                     u32 hl, s_new;
                     lookup_header(tab, win, L.s, hl, s_new);
-                    if (L.entered) sink.block(L.n, L.q, s_new);
+                    if (L.entered) { ck.at_fast(L.q - L.qA, L.s, L.n); sink.block(L.n, L.q, s_new); }
                     L.q += hl + s_new * blk;
                     L.n += 1;
                     L.s = s_new;
@@ -352,6 +369,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_segments_kernel(DecParams p)
     TRPX_SHARED u64 sm_run;
     const u32 t = tid(), lane = t & 31, warp = t >> 5;
     if (t == 0) sm_run = 0;
+    build_header_table<NT>(p.hdr_tab);                       // the walkers copy it into shared memory
     sync_block();
     for (u64 f0 = 0; f0 < p.n_frames; f0 += NT) {
         const u64 f = f0 + t;
@@ -415,7 +433,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_walk_kernel(DecParams p)
     TRPX_DYN_SMEM(sm);
     unsigned short* tab = (unsigned short*)sm;
     u32* buf = (u32*)(sm + HDR_TAB_BYTES) + (tid() >> 5) * WALK_BUF_WORDS;
-    build_header_table<NT>(tab);
+    copy_header_table<NT>(tab, p.hdr_tab);
     sync_block();
     const u64 j = (u64)bid() * NT + tid();
     WalkLane L;
@@ -511,7 +529,17 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_resolve_kernel(DecParams p)
                 if ((u32)k < warp) base += v;
                 total += v;
             }
-            if (i < nseg) p.seg_b0[first + i] = base + incl - c;
+            if (i < nseg) {
+                p.seg_b0[first + i] = base + incl - c;
+                if (p.segd) {
+                    const SegInfo g = seg_info(p, first + i);
+                    u64* d = p.segd + (first + i) * 4;
+                    d[0] = g.base_bit + g.r0;
+                    d[1] = g.base_bit + g.frame_bits;
+                    d[2] = base + incl - c;
+                    d[3] = (u64)(u32)f | (c << 32);
+                }
+            }
             sync_block();
             if (t == 0) sm_run += total;
             sync_block();
@@ -577,7 +605,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_emit_kernel(DecParams p)
     TRPX_DYN_SMEM(sm);
     unsigned short* tab = (unsigned short*)sm;
     u32* buf = (u32*)(sm + HDR_TAB_BYTES) + (tid() >> 5) * WALK_BUF_WORDS;
-    build_header_table<NT>(tab);
+    copy_header_table<NT>(tab, p.hdr_tab);
     sync_block();
     const u64 j = (u64)bid() * NT + tid();
     WalkLane L;
@@ -781,27 +809,37 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(DEC_NT, 1) prolix_unpack_kernel(DecParams p)
 constexpr int UNP_NT = 256;                              // sub-segments (threads) per CTA: 8 KB of stream
 constexpr u32 UNP_TAIL_WORDS = 64;                       // a block that starts in the slice ends inside this tail
 constexpr u32 UNP_SPAN_WORDS = UNP_NT * (SUB_BYTES / 4) + UNP_TAIL_WORDS + 4;
-constexpr u32 UNP_SPAN_PADDED = UNP_SPAN_WORDS + UNP_SPAN_WORDS / SUB_WORDS + 4;
-constexpr u32 UNP_STAGE_BYTES = 48 * 1024;
+// The slice is staged COLUMN-wise: 8-word (32-byte) columns, word r of column c at sp[r * UNP_CP + c].  With a
+// pitch that is a multiple of 32 the bank of an access is its column, so lanes working in different
+// columns never conflict, wherever they are inside their columns.  Rows 8..19 of a column repeat the
+// words of the next columns (r = 8 + k: column c+1 word k; r = 16 + k: column c+2 word k), so a thread
+// reads up to 20 consecutive words of the stream with one multiply-add per access and "next word" is
+// always + UNP_CP.
+constexpr u32 UNP_CP = 288, UNP_ROWS = 20;
+constexpr u32 UNP_SPAN_SMEM_WORDS = UNP_ROWS * UNP_CP;
+constexpr u32 UNP_STAGE_BYTES = 40 * 1024;
 constexpr u32 UNP_SM_TAB = 64;                           // byte offsets inside dynamic shared memory
 constexpr u32 UNP_SM_SPAN = UNP_SM_TAB + HDR_TAB_BYTES;
-constexpr u32 UNP_SM_STAGE = (UNP_SM_SPAN + UNP_SPAN_PADDED * 4 + 127) / 128 * 128;
+constexpr u32 UNP_SM_STAGE = (UNP_SM_SPAN + UNP_SPAN_SMEM_WORDS * 4 + 127) / 128 * 128;
 constexpr u32 UNP_SMEM_BYTES = UNP_SM_STAGE + UNP_STAGE_BYTES + 32;
+static_assert((UNP_SPAN_WORDS + 7) / 8 <= UNP_CP, "columns of the staged slice");
 
-struct SmemBits {                                        // sequential reader over the padded span
+TRPX_DEVICE u32 span_primary(u32 i) { return (i & 7) * UNP_CP + (i >> 3); }   // home of logical word i
+
+struct SmemBits {                                        // sequential reader over the staged slice (any extent)
     const u32* sp;
     u64 acc;
     u32 nb, wi;
     TRPX_DEVICE void init(const u32* sp_, u32 bit)
     {
         sp = sp_; wi = bit >> 5;
-        acc = (u64)sp[wi + (wi >> SUB_WSHIFT)] >> (bit & 31);
+        acc = (u64)sp[span_primary(wi)] >> (bit & 31);
         nb = 32 - (bit & 31);
         ++wi;
     }
     TRPX_DEVICE void fill()                              // afterwards nb >= 32
     {
-        if (nb < 32) { acc |= (u64)sp[wi + (wi >> SUB_WSHIFT)] << nb; nb += 32; ++wi; }
+        if (nb < 32) { acc |= (u64)sp[span_primary(wi)] << nb; nb += 32; ++wi; }
     }
     TRPX_DEVICE void skip(u32 n) { acc >>= n; nb -= n; } // n <= nb
     TRPX_DEVICE u32 get(u32 n)                           // n in [0, 32]
@@ -820,11 +858,11 @@ struct SmemBits {                                        // sequential reader ov
     }
 };
 
-// 32 stream bits starting at bit `pos` of the padded span (two neighbouring words, one funnel shift)
-TRPX_DEVICE u32 span_bits(const u32* sp, u32 pos)
+// 32 stream bits starting `rel` bits into the thread's column (rows 0..19: rel + 32 <= 640)
+TRPX_DEVICE u32 col_bits(const u32* colp, u32 rel)
 {
-    const u32 wi = pos >> 5, pi = wi + (wi >> SUB_WSHIFT);
-    return funnel_r(sp[pi], sp[pi + 1], pos & 31);
+    const u32* w = colp + (rel >> 5) * UNP_CP;
+    return funnel_r(w[0], w[UNP_CP], rel & 31);
 }
 
 template <typename O> struct UnpCap { static constexpr u32 BLOCKS = UNP_STAGE_BYTES / (12 * sizeof(O)); };
@@ -833,10 +871,11 @@ template <typename O> struct UnpCap { static constexpr u32 BLOCKS = UNP_STAGE_BY
 // stores used below).  Every field group is fetched straight from its own bit position: twelve
 // independent extractions, no serial bit-reader state.
 template <typename O, bool SGN>
-TRPX_DEVICE void unpack_block12(const u32* sp, u32 pos, u32 s, O* dst)
+TRPX_DEVICE void unpack_block12(const u32* sp, const u32* colp, u32 rel, u32 pos, u32 s, O* dst)
 {
     constexpr u32 SO = sizeof(O);
-    if (SO == 2 && s <= 16) {
+    const bool in_rows = rel + 12 * s + 32 <= UNP_ROWS * 32;      // the whole block is inside the column's 20 rows
+    if (SO == 2 && s <= 16 && in_rows) {
         // two fields of s bits -> two 16-bit lanes with one multiply-add (the encoder's trick reversed)
         const u32 m2 = s == 16 ? 0xffffffffu : (1u << (2 * s)) - 1;
         const u32 K = 65536u - (1u << s);
@@ -844,7 +883,7 @@ TRPX_DEVICE void unpack_block12(const u32* sp, u32 pos, u32 s, O* dst)
         u32 o[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-            const u32 pm = span_bits(sp, pos + 2 * s * i) & m2;
+            const u32 pm = col_bits(colp, rel + 2 * s * i) & m2;
             u32 x = pm + (pm >> s) * K;
             if (SGN) x |= ((x >> (s - 1)) & 0x00010001u) * KS;
             o[i] = x;
@@ -853,7 +892,7 @@ TRPX_DEVICE void unpack_block12(const u32* sp, u32 pos, u32 s, O* dst)
         d[0] = make_uint2(o[0], o[1]); d[1] = make_uint2(o[2], o[3]); d[2] = make_uint2(o[4], o[5]);
         return;
     }
-    if (SO == 1 && s <= 8) {
+    if (SO == 1 && s <= 8 && in_rows) {
         const u32 m4 = s == 8 ? 0xffffffffu : (1u << (4 * s)) - 1;
         const u32 m2 = (1u << (2 * s)) - 1;
         const u32 K8 = 256u - (1u << s);
@@ -861,7 +900,7 @@ TRPX_DEVICE void unpack_block12(const u32* sp, u32 pos, u32 s, O* dst)
         u32* d = (u32*)dst;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            const u32 q = span_bits(sp, pos + 4 * s * i) & m4;
+            const u32 q = col_bits(colp, rel + 4 * s * i) & m4;
             const u32 p0 = q & m2, p1 = s == 8 ? (q >> 16) : (q >> (2 * s));
             u32 x = (p0 + (p0 >> s) * K8) | ((p1 + (p1 >> s) * K8) << 16);
             if (SGN) x |= ((x >> (s - 1)) & 0x01010101u) * KS;
@@ -869,12 +908,12 @@ TRPX_DEVICE void unpack_block12(const u32* sp, u32 pos, u32 s, O* dst)
         }
         return;
     }
-    if (SO == 4 && s <= 32) {
+    if (SO == 4 && s <= 32 && in_rows) {
         const u32 m = s == 32 ? 0xffffffffu : (1u << s) - 1;
         u32 o[12];
 #pragma unroll
         for (int i = 0; i < 12; ++i) {
-            u32 v = span_bits(sp, pos + s * i) & m;
+            u32 v = col_bits(colp, rel + s * i) & m;
             if (SGN && s < 32 && ((v >> (s - 1)) & 1)) v |= ~0u << s;
             o[i] = v;
         }
@@ -901,21 +940,26 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 1) prolix_unpack_seg_kernel(DecParam
     const u64 j = bid() / parts;
     const u32 h = bid() % parts;
     if (j >= p.seg_base[p.n_frames]) return;
-    const SegInfo g = seg_info(p, j);
-    const u64 b0 = p.seg_b0[j];
+    const u64* sd = p.segd + j * 4;                                  // one level of loads instead of four
+    const u64 seg_bit = sd[0], frame_end_bit = sd[1], b0 = sd[2];
+    const u32 frame = (u32)sd[3], seg_cnt = (u32)(sd[3] >> 32);
     const u32 m = h * UNP_NT + t;                                    // my sub-segment
     const u64* row = p.ckpt + j * p.subs_per_seg;
     // headers of this CTA: [kA, kB) in segment-local numbering, clipped at the frame's last block
-    const u32 seg_cnt = p.seg_count[j];
     const u32 kA = h * UNP_NT < p.subs_per_seg ? ckpt_n(row[h * UNP_NT]) : seg_cnt;
     u32 kB = (h + 1) * UNP_NT < p.subs_per_seg ? ckpt_n(row[(h + 1) * UNP_NT]) : seg_cnt;
+    u64 my_c0 = 0, my_c1 = 0;
+    if (m < p.subs_per_seg) {
+        my_c0 = row[m];
+        my_c1 = m + 1 < p.subs_per_seg ? row[m + 1] : (u64)seg_cnt;
+    }
     if (b0 >= p.nblocks) return;
     if ((u64)kB > p.nblocks - b0) kB = (u32)(p.nblocks - b0);
     if (kA >= kB) return;                                            // uniform: nothing starts in this slice
 
-    build_header_table<UNP_NT>(tab);
+    copy_header_table<UNP_NT>(tab, p.hdr_tab);
     // ---- stage the slice of the stream: 16-byte loads, one pad word per sub-segment
-    const u64 slice_bit = g.base_bit + g.r0 + (u64)h * UNP_NT * SUB_BITS;   // absolute bit of the slice's start (multiple of 8)
+    const u64 slice_bit = seg_bit + (u64)h * UNP_NT * SUB_BITS;       // absolute bit of the slice's start (multiple of 8)
     const u64 a0 = (slice_bit >> 3) & ~15ull;                        // 16-byte aligned byte offset in the payload
     {
         const u64 safe_end = p.payload_bytes & ~15ull;
@@ -933,25 +977,32 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 1) prolix_unpack_seg_kernel(DecParam
                 v.z = wi + 2 < n_words ? p.payload[wi + 2] : 0u;
                 v.w = wi + 3 < n_words ? p.payload[wi + 3] : 0u;
             }
-            const u32 i = 4 * c, pi = i + (i >> SUB_WSHIFT);        // 4 consecutive words never straddle a pad
-            span[pi] = v.x; span[pi + 1] = v.y; span[pi + 2] = v.z; span[pi + 3] = v.w;
-            if ((i & (SUB_WORDS - 1)) == 0 && i) span[pi - 1] = v.x;   // the pad repeats the word after it: word i+1 is always at +1
+            const u32 i = 4 * c, col = i >> 3, r0 = i & 7;                   // 4 words of one column: rows r0 .. r0+3
+            const u32 vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                span[(r0 + q) * UNP_CP + col] = vv[q];
+                if (col >= 1) span[(8 + r0 + q) * UNP_CP + col - 1] = vv[q];
+                if (col >= 2 && r0 == 0) span[(16 + q) * UNP_CP + col - 2] = vv[q];
+            }
         }
     }
 
     // ---- my headers: [k, k_end), the first one at bit `pos` of the span
-    u32 k = 0, k_end = 0, s = 0, pos = 0;
+    u32 k = 0, k_end = 0, s = 0, pos = 0, cbase = 0;
     sync_block();
     if (m < p.subs_per_seg) {
-        const u64 c0 = row[m];
-        k = ckpt_n(c0);
-        k_end = m + 1 < p.subs_per_seg ? ckpt_n(row[m + 1]) : seg_cnt;
+        k = ckpt_n(my_c0);
+        k_end = ckpt_n(my_c1);
         if (k_end > kB) k_end = kB;
-        s = ckpt_s(c0);
-        pos = (u32)(g.base_bit + g.r0 + ckpt_rel(c0) - a0 * 8);
+        s = ckpt_s(my_c0);
+        pos = (u32)(seg_bit + ckpt_rel(my_c0) - a0 * 8);
+        cbase = pos & ~255u;                                         // first bit of the column my first header is in
     }
-    const u32 frame_end_pos = (u32)((g.base_bit + g.frame_bits - a0 * 8 < 0xffffffffull) ? g.base_bit + g.frame_bits - a0 * 8 : 0xffffffffull);
-    O* outf = (O*)p.out + g.frame * p.n_values;
+    const u32* colp = span + (cbase >> 8);
+    const u32 k_last = p.nblocks - 1 - b0 < 0xffffffffull ? (u32)(p.nblocks - 1 - b0) : 0xffffffffu;   // the frame's (possibly ragged) last block
+    const u32 frame_end_pos = (u32)((frame_end_bit - a0 * 8 < 0xffffffffull) ? frame_end_bit - a0 * 8 : 0xffffffffull);
+    O* outf = (O*)p.out + (u64)frame * p.n_values;
     for (u32 c0 = kA; c0 < kB; c0 += CB) {
         const u32 c1 = c0 + CB < kB ? c0 + CB : kB;
         // the chunk's first value in global memory; the stage mirrors its 16-byte phase
@@ -962,15 +1013,14 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 1) prolix_unpack_seg_kernel(DecParam
         while (k < k_end && k < c1) {
             if (pos >= (UNP_NT * SUB_BYTES + 16) * 8) { atomic_max(p.status, DEC_MALFORMED); k = k_end; break; }   // never read past the tail
             u32 hl;
-            lookup_header(tab, span_bits(span, pos), s, hl, s);
+            lookup_header(tab, col_bits(colp, pos - cbase), s, hl, s);   // (a header starts < 384 bits into the column)
             pos += hl;
-            O* dst = (O*)(sbase + (size_t)(k - c0) * 12 * SO);
-            const u32 cnt = b0 + k + 1 == p.nblocks ? p.last_cnt : 12u;
-            if (s > 73) { atomic_max(p.status, DEC_MALFORMED); k = k_end; break; }
+            O* dst = (O*)(sbase + (k - c0) * (12 * SO));
+            const u32 cnt = k == k_last ? p.last_cnt : 12u;      // (s <= 73 by construction of the table)
             if (s == 0) {
                 for (u32 i = 0; i < cnt; ++i) dst[i] = (O)0;
             } else if (cnt == 12) {
-                unpack_block12<O, SGN>(span, pos, s, dst);
+                unpack_block12<O, SGN>(span, colp, pos - cbase, pos, s, dst);
             } else {
                 SmemBits br;
                 br.init(span, pos);
