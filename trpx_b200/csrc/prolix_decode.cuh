@@ -507,6 +507,12 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_resolve_kernel(DecParams p)
         if (!any) break;
         if (sweep > (1u << 22)) trap();
     }
+    // descriptors of table entries past the last segment say "nothing here" (the unpack grid covers max_segs)
+    if (p.segd)
+        for (u64 j = n_segs + gtid; j < p.max_segs; j += gthreads) {
+            u64* d = p.segd + j * 4;
+            d[0] = 0; d[1] = 0; d[2] = 0; d[3] = 0;
+        }
     // ---- per-frame exclusive scan of the block counts (one CTA per frame, frames strided)
     for (u64 f = bid(); f < p.n_frames; f += nblocks()) {
         const u64 first = p.seg_base[f], nseg = p.seg_base[f + 1] - first;
@@ -939,8 +945,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 1) prolix_unpack_seg_kernel(DecParam
     const u32 parts = (p.subs_per_seg + UNP_NT - 1) / UNP_NT;       // CTAs per segment
     const u64 j = bid() / parts;
     const u32 h = bid() % parts;
-    if (j >= p.seg_base[p.n_frames]) return;
-    const u64* sd = p.segd + j * 4;                                  // one level of loads instead of four
+    const u64* sd = p.segd + j * 4;                                  // one level of loads instead of four; count 0 past the last segment
     const u64 seg_bit = sd[0], frame_end_bit = sd[1], b0 = sd[2];
     const u32 frame = (u32)sd[3], seg_cnt = (u32)(sd[3] >> 32);
     const u32 m = h * UNP_NT + t;                                    // my sub-segment
@@ -953,7 +958,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 1) prolix_unpack_seg_kernel(DecParam
         my_c0 = row[m];
         my_c1 = m + 1 < p.subs_per_seg ? row[m + 1] : (u64)seg_cnt;
     }
-    if (b0 >= p.nblocks) return;
+    if (seg_cnt == 0 || b0 >= p.nblocks) return;
     if ((u64)kB > p.nblocks - b0) kB = (u32)(p.nblocks - b0);
     if (kA >= kB) return;                                            // uniform: nothing starts in this slice
 
