@@ -142,7 +142,7 @@ TRPX_DEVICE void mbar_wait_sleep(u64* bar, u32 parity)   // for long, uncritical
 {
     for (u32 spins = 0; !mbar_try_wait(bar, parity); ++spins) {
         if (spins > (1u << 24)) trap();
-        __nanosleep(256);
+        __nanosleep(1000);
     }
 }
 

@@ -138,42 +138,39 @@ TRPX_HD void block_header(u32 s, u32 prev, u32& hv, u32& hl)
 // are resolved by merge_and_flush().
 struct BitSink {
     u32* stg;
-    u64 acc;
+    u32 lo;                 // the unfinished word: nb < 32 valid bits
     u32 w, nb, w0, head;
     bool crossed;
     TRPX_DEVICE void init(u32* stg_, u32 off)
     {
-        stg = stg_; w0 = w = off >> 5; nb = off & 31; acc = 0; head = 0; crossed = false;
+        stg = stg_; w0 = w = off >> 5; nb = off & 31; lo = 0; head = 0; crossed = false;
     }
     TRPX_DEVICE void put(u32 v, u32 n)     // n in [0, 32], v < 2^n
     {
-        acc |= (u64)v << nb;
+        const u32 a0 = lo | (v << nb);
+        const u32 a1 = funnel_l(v, 0u, nb);                     // v >> (32 - nb); 0 when nb == 0
         nb += n;
-        if (nb >= 32) {
-            u32 lo = (u32)acc;
-            if (!crossed) { head = lo; crossed = true; } else stg[w] = lo;
-            ++w;
-            acc >>= 32;
-            nb -= 32;
-        }
+        const bool p1 = nb >= 32;
+        if (p1) { if (crossed) stg[w] = a0; else head = a0; }
+        crossed = crossed || p1;
+        lo = p1 ? a1 : a0;
+        w += p1 ? 1u : 0u;
+        nb &= 31;
     }
-    // n in [0, 64], v < 2^n.  Same contract as put(); up to two words complete per call.  Written
-    // without data-dependent branches so that lanes with different widths stay converged.
+    // n in [0, 64], v < 2^n.  Same contract as put(); up to two words complete per call.  Straight-line
+    // code (selects and predicated stores), so lanes with different widths stay converged.
     TRPX_DEVICE void put64(u64 v, u32 n)
     {
-        const u32 ov = funnel_l((u32)(v >> 32), 0u, nb);       // bits pushed past bit 63 (nb < 32)
-        acc |= v << nb;
+        const u32 v0 = (u32)v, v1 = (u32)(v >> 32);
+        const u32 a0 = lo | (v0 << nb);                         // bits  0..31 of lo | v << nb
+        const u32 a1 = funnel_l(v0, v1, nb);                    // bits 32..63
+        const u32 a2 = funnel_l(v1, 0u, nb);                    // bits 64..95
         nb += n;
         const u32 c = nb >> 5;                                  // complete words: 0, 1 or 2
-        const u32 a0 = (u32)acc, a1 = (u32)(acc >> 32);
-        if (c >= 1) {
-            if (!crossed) head = a0; else stg[w] = a0;
-            if (c >= 2) stg[w + 1] = a1;
-            crossed = true;
-        }
-        const u32 n0 = c == 0 ? a0 : (c == 1 ? a1 : ov);
-        const u32 n1 = c == 0 ? a1 : (c == 1 ? ov : 0u);
-        acc = (u64)n0 | ((u64)n1 << 32);
+        if (c >= 1) { if (crossed) stg[w] = a0; else head = a0; }
+        if (c >= 2) stg[w + 1] = a1;
+        crossed = crossed || c >= 1;
+        lo = c == 0 ? a0 : (c == 1 ? a1 : a2);
         w += c;
         nb &= 31;
     }
@@ -289,7 +286,7 @@ TRPX_DEVICE void zero_boundary_words(u32* stg, u32 off, u32 tile_bits)
 TRPX_DEVICE void merge_and_flush(BitSink& sk, u32 end_off)
 {
     const u32 lane = tid() & 31;
-    const u32 tail = (u32)sk.acc;
+    const u32 tail = sk.lo;
     u32 incl = tail;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -516,7 +513,7 @@ struct EncGeom {
     // for a typical 512^2 u16 tile, WORST_WORDS when nothing compresses.  The ring always holds two
     // worst-case tiles; with typical data ENC_DEPTH tiles are in flight.
     static constexpr int WORST_WORDS = ((TILE_BLOCKS * P::MAXBITS + 31) / 32 + 1 + 3 + 3) / 4 * 4;
-    static constexpr int RING_WORDS = 2 * WORST_WORDS > 9216 ? 2 * WORST_WORDS : 9216;
+    static constexpr int RING_WORDS = 2 * WORST_WORDS <= 8192 ? 8192 : (2 * WORST_WORDS <= 16384 ? 16384 : 32768);   // a power of two
     static constexpr int SMEM_BYTES = SM_HEADER + ENC_STAGES * STAGE_BYTES + RING_WORDS * 4;
     static constexpr int THREADS = NT + 32 * ENC_RESOLVERS;   // worker warps + resolver warps
 };
@@ -635,7 +632,8 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_RESOLVERS, 3) terse_encode_ker
     // ring bookkeeping, identical in every worker thread: virtual word offsets that only grow; the
     // tiles of iterations [oldest, it) are packed but not stored and occupy [vtail, vhead)
     u32 vhead = 0, vtail = 0, oldest = 0;
-    const u32 ring_words = p.dbg_ring_words ? p.dbg_ring_words : (u32)G::RING_WORDS;   // tests shrink the ring
+    const u32 ring_words = p.dbg_ring_words ? p.dbg_ring_words : (u32)G::RING_WORDS;   // a power of two (tests vary it)
+    const u32 ring_mask = ring_words - 1;
     u32 my_max = 0;
     u32 it = 0;
     for (;; ++it) {
@@ -719,7 +717,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_RESOLVERS, 3) terse_encode_ker
         // words -1 .. (bits/32)+2: a frame end may push the window one word past the zero pad (tail_handoff)
         const u32 need = ((tile_bits >> 5) + 1 + 3 + 3) & ~3u;
         u32 vbase = vhead;
-        if (vbase % ring_words + need > ring_words) vbase += ring_words - vbase % ring_words;
+        if ((vbase & ring_mask) + need > ring_words) vbase += ring_words - (vbase & ring_mask);
         bool stored = false;
         while (it - oldest == (u32)ENC_DEPTH || (it > oldest && vbase + need - vtail > ring_words)) {
             store_pending(oldest);                         // blocks only if that resolution is really late
@@ -728,12 +726,12 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_RESOLVERS, 3) terse_encode_ker
             stored = true;
         }
         if (stored) bar_sync(1, NT);                       // E: freed ring words and mailbox entries are reusable
-        u32* stg = ring + vbase % ring_words + 1;
+        u32* stg = ring + (vbase & ring_mask) + 1;
         if (t == 0) {
             mail64[e * 4] = tile;
             vbases[e] = vbase;
             mail32[e * 8 + 4] = tile_bits;
-            mail32[e * 8 + 7] = vbase % ring_words + 1;
+            mail32[e * 8 + 7] = (vbase & ring_mask) + 1;
             stg[-1] = 0;
             mbar_arrive(&bar_ready[e]);                    // the resolver may start its look-back
         }
