@@ -932,47 +932,47 @@ TRPX_DEVICE void unpack_block12(const u32* sp, const u32* colp, u32 rel, u32 pos
     for (u32 i = 0; i < 12; ++i) dst[i] = convert_value<O, SGN>(s <= 32 ? (u64)br.get(s) : br.get_wide(s), s);
 }
 
-template <typename O, bool SGN>
-TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 1) prolix_unpack_seg_kernel(DecParams p)
-{
-    constexpr u32 SO = sizeof(O);
-    constexpr u32 CB = UnpCap<O>::BLOCKS;
-    TRPX_DYN_SMEM(sm);
-    unsigned short* tab = (unsigned short*)(sm + UNP_SM_TAB);
-    u32* span = (u32*)(sm + UNP_SM_SPAN);
-    unsigned char* stage = sm + UNP_SM_STAGE;
-    const u32 t = tid();
-    const u32 parts = (p.subs_per_seg + UNP_NT - 1) / UNP_NT;       // CTAs per segment
-    const u64 j = bid() / parts;
-    const u32 h = bid() % parts;
-    const u64* sd = p.segd + j * 4;                                  // one level of loads instead of four; count 0 past the last segment
-    const u64 seg_bit = sd[0], frame_end_bit = sd[1], b0 = sd[2];
-    const u32 frame = (u32)sd[3], seg_cnt = (u32)(sd[3] >> 32);
-    const u32 m = h * UNP_NT + t;                                    // my sub-segment
-    const u64* row = p.ckpt + j * p.subs_per_seg;
-    // headers of this CTA: [kA, kB) in segment-local numbering, clipped at the frame's last block
-    const u32 kA = h * UNP_NT < p.subs_per_seg ? ckpt_n(row[h * UNP_NT]) : seg_cnt;
-    u32 kB = (h + 1) * UNP_NT < p.subs_per_seg ? ckpt_n(row[(h + 1) * UNP_NT]) : seg_cnt;
-    u64 my_c0 = 0, my_c1 = 0;
-    if (m < p.subs_per_seg) {
-        my_c0 = row[m];
-        my_c1 = m + 1 < p.subs_per_seg ? row[m + 1] : (u64)seg_cnt;
-    }
-    if (seg_cnt == 0 || b0 >= p.nblocks) return;
-    if ((u64)kB > p.nblocks - b0) kB = (u32)(p.nblocks - b0);
-    if (kA >= kB) return;                                            // uniform: nothing starts in this slice
+// What a thread needs to know about one slice (a CTA's 8 KB of stream); loaded two slices ahead.
+struct SliceDesc {
+    u64 seg_bit, frame_end_bit, b0;     // CTA-uniform: segment start (absolute bit), frame end, first block of the segment
+    u32 frame, seg_cnt, h;
+    u64 rowA, rowB;                     // checkpoints that bound the CTA's headers
+    u64 c0, c1;                         // this thread's checkpoint and the next one
+};
+constexpr u32 UNP_CHUNKS = (UNP_SPAN_WORDS / 4 + UNP_NT - 1) / UNP_NT;    // 16-byte pieces of the slice per thread
 
-    copy_header_table<UNP_NT>(tab, p.hdr_tab);
-    // ---- stage the slice of the stream: 16-byte loads, one pad word per sub-segment
-    const u64 slice_bit = seg_bit + (u64)h * UNP_NT * SUB_BITS;       // absolute bit of the slice's start (multiple of 8)
-    const u64 a0 = (slice_bit >> 3) & ~15ull;                        // 16-byte aligned byte offset in the payload
-    {
-        const u64 safe_end = p.payload_bytes & ~15ull;
-        const u64 n_words = (p.payload_bytes + 3) >> 2;
-        const unsigned char* base = (const unsigned char*)p.payload;
-        for (u32 c = t; c < UNP_SPAN_WORDS / 4; c += UNP_NT) {
-            const u64 b = a0 + 16ull * c;
-            uint4 v = make_uint4(0, 0, 0, 0);
+TRPX_DEVICE SliceDesc load_slice_desc(const DecParams& p, u32 sl, u32 parts)
+{
+    SliceDesc d;
+    const u64 j = sl / parts;
+    d.h = sl % parts;
+    const u64* sd = p.segd + j * 4;                                  // count 0 past the last segment
+    d.seg_bit = sd[0]; d.frame_end_bit = sd[1]; d.b0 = sd[2];
+    const u64 fc = sd[3];
+    d.frame = (u32)fc; d.seg_cnt = (u32)(fc >> 32);
+    const u64* row = p.ckpt + j * p.subs_per_seg;
+    const u32 m = d.h * UNP_NT + tid();
+    d.rowA = d.h * UNP_NT < p.subs_per_seg ? row[d.h * UNP_NT] : ~0ull;
+    d.rowB = (d.h + 1) * UNP_NT < p.subs_per_seg ? row[(d.h + 1) * UNP_NT] : ~0ull;
+    d.c0 = m < p.subs_per_seg ? row[m] : ~0ull;
+    d.c1 = m + 1 < p.subs_per_seg ? row[m + 1] : ~0ull;
+    return d;
+}
+TRPX_DEVICE u64 slice_a0(const SliceDesc& d)      // 16-byte aligned byte offset of the slice's first word in the payload
+{
+    return ((d.seg_bit + (u64)d.h * UNP_NT * SUB_BITS) >> 3) & ~15ull;
+}
+TRPX_DEVICE void fetch_slice(const DecParams& p, u64 a0, uint4 (&pre)[UNP_CHUNKS])
+{
+    const u64 safe_end = p.payload_bytes & ~15ull;
+    const u64 n_words = (p.payload_bytes + 3) >> 2;
+    const unsigned char* base = (const unsigned char*)p.payload;
+#pragma unroll
+    for (u32 q = 0; q < UNP_CHUNKS; ++q) {
+        const u32 c = tid() + q * UNP_NT;
+        const u64 b = a0 + 16ull * c;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (c < UNP_SPAN_WORDS / 4) {
             if (b + 16 <= safe_end) {
                 v = *(const uint4*)(base + b);
             } else if (b < p.payload_bytes) {
@@ -982,75 +982,132 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 1) prolix_unpack_seg_kernel(DecParam
                 v.z = wi + 2 < n_words ? p.payload[wi + 2] : 0u;
                 v.w = wi + 3 < n_words ? p.payload[wi + 3] : 0u;
             }
-            const u32 i = 4 * c, col = i >> 3, r0 = i & 7;                   // 4 words of one column: rows r0 .. r0+3
-            const u32 vv[4] = {v.x, v.y, v.z, v.w};
+        }
+        pre[q] = v;
+    }
+}
+TRPX_DEVICE void stage_slice(u32* span, const uint4 (&pre)[UNP_CHUNKS])
+{
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                span[(r0 + q) * UNP_CP + col] = vv[q];
-                if (col >= 1) span[(8 + r0 + q) * UNP_CP + col - 1] = vv[q];
-                if (col >= 2 && r0 == 0) span[(16 + q) * UNP_CP + col - 2] = vv[q];
+    for (u32 q = 0; q < UNP_CHUNKS; ++q) {
+        const u32 c = tid() + q * UNP_NT;
+        if (c < UNP_SPAN_WORDS / 4) {
+            const u32 i = 4 * c, col = i >> 3, r0 = i & 7;           // 4 words of one column: rows r0 .. r0+3
+            const u32 vv[4] = {pre[q].x, pre[q].y, pre[q].z, pre[q].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                span[(r0 + e) * UNP_CP + col] = vv[e];
+                if (col >= 1) span[(8 + r0 + e) * UNP_CP + col - 1] = vv[e];
+                if (col >= 2 && r0 == 0) span[(16 + e) * UNP_CP + col - 2] = vv[e];
             }
         }
     }
+}
 
-    // ---- my headers: [k, k_end), the first one at bit `pos` of the span
-    u32 k = 0, k_end = 0, s = 0, pos = 0, cbase = 0;
-    sync_block();
-    if (m < p.subs_per_seg) {
-        k = ckpt_n(my_c0);
-        k_end = ckpt_n(my_c1);
-        if (k_end > kB) k_end = kB;
-        s = ckpt_s(my_c0);
-        pos = (u32)(seg_bit + ckpt_rel(my_c0) - a0 * 8);
-        cbase = pos & ~255u;                                         // first bit of the column my first header is in
-    }
-    const u32* colp = span + (cbase >> 8);
-    const u32 k_last = p.nblocks - 1 - b0 < 0xffffffffull ? (u32)(p.nblocks - 1 - b0) : 0xffffffffu;   // the frame's (possibly ragged) last block
-    const u32 frame_end_pos = (u32)((frame_end_bit - a0 * 8 < 0xffffffffull) ? frame_end_bit - a0 * 8 : 0xffffffffull);
-    O* outf = (O*)p.out + (u64)frame * p.n_values;
-    for (u32 c0 = kA; c0 < kB; c0 += CB) {
-        const u32 c1 = c0 + CB < kB ? c0 + CB : kB;
-        // the chunk's first value in global memory; the stage mirrors its 16-byte phase
-        const u64 v0 = (b0 + c0) * 12;
-        unsigned char* gdst = (unsigned char*)(outf + v0);
-        const u32 phase = (u32)((uintptr_t)gdst & 15);
-        unsigned char* sbase = stage + phase;
-        while (k < k_end && k < c1) {
-            if (pos >= (UNP_NT * SUB_BYTES + 16) * 8) { atomic_max(p.status, DEC_MALFORMED); k = k_end; break; }   // never read past the tail
-            u32 hl;
-            lookup_header(tab, col_bits(colp, pos - cbase), s, hl, s);   // (a header starts < 384 bits into the column)
-            pos += hl;
-            O* dst = (O*)(sbase + (k - c0) * (12 * SO));
-            const u32 cnt = k == k_last ? p.last_cnt : 12u;      // (s <= 73 by construction of the table)
-            if (s == 0) {
-                for (u32 i = 0; i < cnt; ++i) dst[i] = (O)0;
-            } else if (cnt == 12) {
-                unpack_block12<O, SGN>(span, colp, pos - cbase, pos, s, dst);
-            } else {
-                SmemBits br;
-                br.init(span, pos);
-                for (u32 i = 0; i < cnt; ++i) dst[i] = convert_value<O, SGN>(s <= 32 ? (u64)br.get(s) : br.get_wide(s), s);
+// Persistent CTAs: slice i is unpacked while the stream of slice i+1 and the descriptors of slice i+2 are in flight.
+template <typename O, bool SGN>
+TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 3) prolix_unpack_seg_kernel(DecParams p)
+{
+    constexpr u32 SO = sizeof(O);
+    constexpr u32 CB = UnpCap<O>::BLOCKS;
+    TRPX_DYN_SMEM(sm);
+    unsigned short* tab = (unsigned short*)(sm + UNP_SM_TAB);
+    u32* span = (u32*)(sm + UNP_SM_SPAN);
+    unsigned char* stage = sm + UNP_SM_STAGE;
+    const u32 t = tid();
+    const u32 parts = (p.subs_per_seg + UNP_NT - 1) / UNP_NT;       // slices per segment
+    const u64 total64 = p.max_segs * parts;
+    const u32 total = total64 < 0xffffffffull ? (u32)total64 : 0xffffffffu;
+    const u32 step = nblocks();
+    u32 sl = bid();
+    if (sl >= total) return;
+    copy_header_table<UNP_NT>(tab, p.hdr_tab);
+
+    SliceDesc d0 = load_slice_desc(p, sl, parts), d1 = d0, d2 = d0;
+    if (sl + step < total && sl + step >= sl) d1 = load_slice_desc(p, sl + step, parts);
+    uint4 pre[UNP_CHUNKS];
+    fetch_slice(p, slice_a0(d0), pre);
+    for (;;) {
+        const bool have1 = sl + step < total && sl + step >= sl;
+        const bool have2 = have1 && sl + 2 * step < total && sl + 2 * step >= sl + step;
+        if (have2) d2 = load_slice_desc(p, sl + 2 * step, parts);   // arrives during this iteration
+        const u64 a0 = slice_a0(d0);
+        stage_slice(span, pre);                                     // (the previous iteration ended with a barrier)
+        sync_block();
+        if (have1) fetch_slice(p, slice_a0(d1), pre);               // in flight while this slice is unpacked
+
+        // ---- headers of this CTA: [kA, kB) in segment-local numbering, clipped at the frame's last block
+        const u32 kA = d0.rowA != ~0ull ? ckpt_n(d0.rowA) : d0.seg_cnt;
+        u32 kB = d0.rowB != ~0ull ? ckpt_n(d0.rowB) : d0.seg_cnt;
+        const bool live = d0.seg_cnt != 0 && d0.b0 < p.nblocks;
+        if (live && (u64)kB > p.nblocks - d0.b0) kB = (u32)(p.nblocks - d0.b0);
+        if (live && kA < kB) {
+            // ---- my headers: [k, k_end), the first one at bit `pos` of the span
+            u32 k = 0, k_end = 0, s = 0, pos = 0, cbase = 0;
+            if (d0.c0 != ~0ull) {
+                k = ckpt_n(d0.c0);
+                k_end = d0.c1 != ~0ull ? ckpt_n(d0.c1) : d0.seg_cnt;
+                if (k_end > kB) k_end = kB;
+                s = ckpt_s(d0.c0);
+                pos = (u32)(d0.seg_bit + ckpt_rel(d0.c0) - a0 * 8);
+                cbase = pos & ~255u;                                 // first bit of the column my first header is in
             }
-            pos += s * cnt;
-            ++k;
-            if (k == k_end && pos > frame_end_pos) atomic_max(p.status, DEC_MALFORMED);   // the last block runs past the frame's end
+            const u32* colp = span + (cbase >> 8);
+            const u64 b0 = d0.b0;
+            const u32 k_last = p.nblocks - 1 - b0 < 0xffffffffull ? (u32)(p.nblocks - 1 - b0) : 0xffffffffu;   // the frame's (possibly ragged) last block
+            const u32 frame_end_pos = (u32)((d0.frame_end_bit - a0 * 8 < 0xffffffffull) ? d0.frame_end_bit - a0 * 8 : 0xffffffffull);
+            O* outf = (O*)p.out + (u64)d0.frame * p.n_values;
+            for (u32 c0 = kA; c0 < kB; c0 += CB) {
+                const u32 c1 = c0 + CB < kB ? c0 + CB : kB;
+                // the chunk's first value in global memory; the stage mirrors its 16-byte phase
+                const u64 v0 = (b0 + c0) * 12;
+                unsigned char* gdst = (unsigned char*)(outf + v0);
+                const u32 phase = (u32)((uintptr_t)gdst & 15);
+                unsigned char* sbase = stage + phase;
+                while (k < k_end && k < c1) {
+                    if (pos >= (UNP_NT * SUB_BYTES + 16) * 8) { atomic_max(p.status, DEC_MALFORMED); k = k_end; break; }   // never read past the tail
+                    u32 hl;
+                    lookup_header(tab, col_bits(colp, pos - cbase), s, hl, s);   // (a header starts < 384 bits into the column)
+                    pos += hl;
+                    O* dst = (O*)(sbase + (k - c0) * (12 * SO));
+                    const u32 cnt = k == k_last ? p.last_cnt : 12u;      // (s <= 73 by construction of the table)
+                    if (s == 0) {
+                        for (u32 i = 0; i < cnt; ++i) dst[i] = (O)0;
+                    } else if (cnt == 12) {
+                        unpack_block12<O, SGN>(span, colp, pos - cbase, pos, s, dst);
+                    } else {
+                        SmemBits br;
+                        br.init(span, pos);
+                        for (u32 i = 0; i < cnt; ++i) dst[i] = convert_value<O, SGN>(s <= 32 ? (u64)br.get(s) : br.get_wide(s), s);
+                    }
+                    pos += s * cnt;
+                    ++k;
+                    if (k == k_end && pos > frame_end_pos) atomic_max(p.status, DEC_MALFORMED);   // the last block runs past the frame's end
+                }
+                fence_async_smem();
+                sync_block();
+                // ---- store [v0, v1): unaligned head and tail bytes by hand, the 16-byte aligned middle as one bulk copy
+                const u64 v1 = (b0 + c1) * 12 < p.n_values ? (b0 + c1) * 12 : p.n_values;
+                const u32 bytes = (u32)((v1 - v0) * SO);
+                u32 head = (16 - phase) & 15;
+                if (head > bytes) head = bytes;
+                const u32 mid = (bytes - head) & ~15u;
+                for (u32 i = t; i < head; i += UNP_NT) gdst[i] = sbase[i];
+                for (u32 i = head + mid + t; i < bytes; i += UNP_NT) gdst[i] = sbase[i];
+                if (t == 0 && mid) {
+                    bulk_s2g(gdst + head, sbase + head, mid);
+                    bulk_commit();
+                    bulk_wait_read0();
+                }
+                sync_block();
+            }
+        } else {
+            sync_block();                                           // everybody has staged before the span is overwritten
         }
-        fence_async_smem();
-        sync_block();
-        // ---- store [v0, v1): unaligned head and tail bytes by hand, the 16-byte aligned middle as one bulk copy
-        const u64 v1 = (b0 + c1) * 12 < p.n_values ? (b0 + c1) * 12 : p.n_values;
-        const u32 bytes = (u32)((v1 - v0) * SO);
-        u32 head = (16 - phase) & 15;
-        if (head > bytes) head = bytes;
-        const u32 mid = (bytes - head) & ~15u;
-        for (u32 i = t; i < head; i += UNP_NT) gdst[i] = sbase[i];
-        for (u32 i = head + mid + t; i < bytes; i += UNP_NT) gdst[i] = sbase[i];
-        if (t == 0 && mid) {
-            bulk_s2g(gdst + head, sbase + head, mid);
-            bulk_commit();
-            bulk_wait_read0();
-        }
-        sync_block();
+        if (!have1) break;
+        sl += step;
+        d0 = d1;
+        d1 = d2;
     }
 }
 

@@ -138,12 +138,24 @@ TRPX_DEVICE void mbar_wait(u64* bar, u32 parity)
         if (spins > (1u << 26)) trap();
 }
 
-TRPX_DEVICE void mbar_wait_sleep(u64* bar, u32 parity)   // for long, uncritical waits
+// For long, uncritical waits (the resolver warps are idle most of the time): let the hardware suspend
+// the thread inside try_wait for up to `hint` ns instead of burning issue slots in a spin loop.
+TRPX_DEVICE bool mbar_try_wait_hint(u64* bar, u32 parity, u32 hint_ns)
 {
-    for (u32 spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+    u32 ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_addr(bar)), "r"(parity), "r"(hint_ns)
+        : "memory");
+    return ok != 0;
+}
+TRPX_DEVICE void mbar_wait_sleep(u64* bar, u32 parity)
+{
+    for (u32 spins = 0; !mbar_try_wait_hint(bar, parity, 200000u); ++spins)
         if (spins > (1u << 24)) trap();
-        __nanosleep(1000);
-    }
 }
 
 // ---- TMA bulk copies (1-D): SASS UBLKCP ----
