@@ -13,6 +13,7 @@
 #include <sstream>
 #include <vector>
 
+#include <trpx/Grey_tiff_io.hpp>
 #include <trpx/Terse.hpp>
 
 static int fails = 0;
@@ -39,6 +40,17 @@ static int container_mode(const char* in, const char* out)
     std::printf("\n");
     std::ofstream os(out, std::ios::binary);
     t.write(os);
+    return 0;
+}
+
+static int tiff_mode(const char* in, const char* out)       // host only: TIFF stack -> TIFF stack through Grey_tiff_io
+{
+    std::ifstream is(in, std::ios::binary);
+    auto imgs = jpa::tiffio::read(is);
+    for (auto const& im : imgs)
+        std::printf("image %zux%zu bits=%u kind=%d\n", im.width, im.height, im.bits, int(im.kind));
+    std::ofstream os(out, std::ios::binary);
+    jpa::tiffio::write(os, imgs);
     return 0;
 }
 
@@ -109,6 +121,7 @@ int main(int argc, char** argv)
 {
     try {
         if (argc == 4 && !std::strcmp(argv[1], "--container")) return container_mode(argv[2], argv[3]);
+        if (argc == 4 && !std::strcmp(argv[1], "--tiff")) return tiff_mode(argv[2], argv[3]);
         if (argc == 2 && !std::strcmp(argv[1], "--gpu")) return gpu_mode();
     } catch (std::exception const& e) {
         std::printf("exception: %s\n", e.what());

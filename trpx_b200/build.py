@@ -43,7 +43,9 @@ def build(force=False, verbose=False):
 
 
 ROOT = os.path.dirname(HERE)
-HOST_TARGETS = {"terse_selftest": [os.path.join(ROOT, "cxx", "terse_selftest.cpp")]}
+HOST_TARGETS = {"terse_selftest": [os.path.join(ROOT, "cxx", "terse_selftest.cpp")],
+                "terse": [os.path.join(ROOT, "cxx", "terse.cpp")],
+                "prolix": [os.path.join(ROOT, "cxx", "prolix.cpp")]}
 
 
 def build_host(force=False):
@@ -55,7 +57,8 @@ def build_host(force=False):
         if not srcs:
             continue
         out = os.path.join(ROOT, "cxx", name)
-        deps = srcs + [os.path.join(ROOT, "include", "trpx", "Terse.hpp"), os.path.join(ROOT, "include", "trpx_b200.h"), OUT]
+        deps = srcs + [os.path.join(ROOT, "include", "trpx", "Terse.hpp"), os.path.join(ROOT, "include", "trpx", "Grey_tiff_io.hpp"),
+                       os.path.join(ROOT, "include", "trpx_b200.h"), OUT]
         if force or not os.path.exists(out) or any(os.path.getmtime(out) < os.path.getmtime(d) for d in deps if os.path.exists(d)):
             cmd = [cxx, "-std=c++20", "-O2", "-DNDEBUG", "-Wall", "-I", os.path.join(ROOT, "include")] + srcs + [
                 "-L", HERE, "-ltrpx_b200", "-Wl,-rpath," + HERE, "-o", out]
