@@ -102,6 +102,21 @@ def test_c2_shape_frames(codec):
     roundtrip(codec, st[:3], known_sizes=False)
 
 
+def test_foreign_stack_frame_sizes_are_recovered_from_the_stream(codec):
+    """A multi-frame payload as it comes out of a .trpx file: only the total size is known (Terse.hpp:459)."""
+    import time
+    st = np.stack([orc.synth_frame(orc.U16, 512, 512, 2.0, 100, 5000 + f) for f in range(48)])
+    st[7] = 0                                                      # an empty frame: one long run of 1-bit blocks
+    p, fb, pb = codec.encode(st)
+    t0 = time.time()
+    d, fb2 = codec.decode(p, st.shape[1], st.shape[0], False, np.uint16)
+    dt = time.time() - t0
+    assert np.array_equal(fb2, fb) and np.array_equal(d, st)
+    assert dt < 5.0, "frame-boundary recovery took %.1f s" % dt
+    d, _ = codec.decode(p, st.shape[1], st.shape[0], False, np.uint16, first_frame=40, n_frames=3)
+    assert np.array_equal(d, st[40:43])
+
+
 def test_signed_dark_subtracted_frames(codec):
     for dt in (orc.I16, orc.I32):
         st = np.stack([orc.synth_frame(dt, 512, 512, 3.0, 0, 77 + f) for f in range(6)])
