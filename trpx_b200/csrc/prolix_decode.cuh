@@ -932,6 +932,8 @@ TRPX_DEVICE void unpack_block12(const u32* sp, const u32* colp, u32 rel, u32 pos
     for (u32 i = 0; i < 12; ++i) dst[i] = convert_value<O, SGN>(s <= 32 ? (u64)br.get(s) : br.get_wide(s), s);
 }
 
+TRPX_HD u32 umin3(u32 a, u32 b, u32 c) { const u32 m = a < b ? a : b; return m < c ? m : c; }
+
 // What a thread needs to know about one slice (a CTA's 8 KB of stream); loaded two slices ahead.
 struct SliceDesc {
     u64 seg_bit, frame_end_bit, b0;     // CTA-uniform: segment start (absolute bit), frame end, first block of the segment
@@ -1052,6 +1054,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 3) prolix_unpack_seg_kernel(DecParam
                 pos = (u32)(d0.seg_bit + ckpt_rel(d0.c0) - a0 * 8);
                 cbase = pos & ~255u;                                 // first bit of the column my first header is in
             }
+            const u32 k_begin = k;
             const u32* colp = span + (cbase >> 8);
             const u64 b0 = d0.b0;
             const u32 k_last = p.nblocks - 1 - b0 < 0xffffffffull ? (u32)(p.nblocks - 1 - b0) : 0xffffffffu;   // the frame's (possibly ragged) last block
@@ -1064,26 +1067,36 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 3) prolix_unpack_seg_kernel(DecParam
                 unsigned char* gdst = (unsigned char*)(outf + v0);
                 const u32 phase = (u32)((uintptr_t)gdst & 15);
                 unsigned char* sbase = stage + phase;
-                while (k < k_end && k < c1) {
-                    if (pos >= (UNP_NT * SUB_BYTES + 16) * 8) { atomic_max(p.status, DEC_MALFORMED); k = k_end; break; }   // never read past the tail
+                // full blocks (12 values) in a tight loop; the frame's ragged last block, if it is mine, afterwards
+                const u32 stop_full = umin3(k_end, c1, k_last);
+                while (k < stop_full) {
                     u32 hl;
                     lookup_header(tab, col_bits(colp, pos - cbase), s, hl, s);   // (a header starts < 384 bits into the column)
                     pos += hl;
                     O* dst = (O*)(sbase + (k - c0) * (12 * SO));
-                    const u32 cnt = k == k_last ? p.last_cnt : 12u;      // (s <= 73 by construction of the table)
                     if (s == 0) {
-                        for (u32 i = 0; i < cnt; ++i) dst[i] = (O)0;
-                    } else if (cnt == 12) {
-                        unpack_block12<O, SGN>(span, colp, pos - cbase, pos, s, dst);
+#pragma unroll
+                        for (u32 i = 0; i < 12; ++i) dst[i] = (O)0;
                     } else {
-                        SmemBits br;
-                        br.init(span, pos);
-                        for (u32 i = 0; i < cnt; ++i) dst[i] = convert_value<O, SGN>(s <= 32 ? (u64)br.get(s) : br.get_wide(s), s);
+                        unpack_block12<O, SGN>(span, colp, pos - cbase, pos, s, dst);
                     }
-                    pos += s * cnt;
+                    pos += s * 12;
                     ++k;
-                    if (k == k_end && pos > frame_end_pos) atomic_max(p.status, DEC_MALFORMED);   // the last block runs past the frame's end
+                    if (k < stop_full && pos >= (UNP_NT * SUB_BYTES + 16) * 8) { atomic_max(p.status, DEC_MALFORMED); k = k_end; break; }   // never read a header past the tail
                 }
+                if (k == k_last && k < k_end && k < c1) {           // the (possibly ragged) last block of the frame
+                    u32 hl;
+                    lookup_header(tab, col_bits(colp, pos - cbase), s, hl, s);
+                    pos += hl;
+                    O* dst = (O*)(sbase + (k - c0) * (12 * SO));
+                    SmemBits br;
+                    br.init(span, pos);
+                    for (u32 i = 0; i < p.last_cnt; ++i)
+                        dst[i] = s == 0 ? (O)0 : convert_value<O, SGN>(s <= 32 ? (u64)br.get(s) : br.get_wide(s), s);
+                    pos += s * p.last_cnt;
+                    ++k;
+                }
+                if (k == k_end && k_end > k_begin && pos > frame_end_pos) atomic_max(p.status, DEC_MALFORMED);   // my last block runs past the frame's end
                 fence_async_smem();
                 sync_block();
                 // ---- store [v0, v1): unaligned head and tail bytes by hand, the 16-byte aligned middle as one bulk copy
