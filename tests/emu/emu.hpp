@@ -78,6 +78,12 @@ inline void bar_sync(uint32_t id, uint32_t n)
     else while (s.nbar_gen[id & 15] == gen) yield();
 }
 
+inline void bar_arrive(uint32_t id, uint32_t n)
+{
+    State& s = S();
+    if (++s.nbar_count[id & 15] == n) { s.nbar_count[id & 15] = 0; ++s.nbar_gen[id & 15]; progress(); }
+}
+
 inline void sync_warp()
 {
     State& s = S();

@@ -44,6 +44,9 @@ TRPX_DEVICE void sync_warp() { __syncwarp(); }
 // named barrier `id` (1..15) over `n` threads (a multiple of 32): lets the worker warps of a
 // warp-specialised CTA synchronise among themselves without the resolver warps
 TRPX_DEVICE void bar_sync(u32 id, u32 n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+// producer side of a named barrier: counts the calling warp(s) in without waiting; the consumer blocks in
+// bar_sync() -- a hardware wait, no spin loop
+TRPX_DEVICE void bar_arrive(u32 id, u32 n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 TRPX_DEVICE void spin_hint() { __nanosleep(32); }
 TRPX_DEVICE void trap() { __trap(); }
 
@@ -224,6 +227,7 @@ inline u32 nblocks() { return ::emu::cur().grid_dim; }
 inline void sync_block() { ::emu::sync_block(); }
 inline void sync_warp() { ::emu::sync_warp(); }
 inline void bar_sync(u32 id, u32 n) { ::emu::bar_sync(id, n); }
+inline void bar_arrive(u32 id, u32 n) { ::emu::bar_arrive(id, n); }
 inline void spin_hint() { ::emu::yield(); }
 inline void trap() { ::emu::trap(); }
 

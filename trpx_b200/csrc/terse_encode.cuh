@@ -491,6 +491,7 @@ constexpr int ENC_STAGES = 2;       // TMA pixel stages
 constexpr int ENC_DEPTH = 6;        // tiles a CTA may have packed but not yet stored (mailbox entries)
 constexpr int ENC_RESOLVERS = 2;    // resolver warps; resolver r serves iterations it % ENC_RESOLVERS == r
 static_assert(ENC_DEPTH % ENC_RESOLVERS == 0, "a mailbox entry is always served by the same resolver");
+static_assert(2 + 2 * ENC_DEPTH <= 16, "named barriers: 0 CTA, 1 workers, 2.. ready, 2+DEPTH.. packed");
 constexpr int SM_BARS = 0;          // mbarriers, 8 bytes each: full[STAGES], ready[DEPTH], packed[DEPTH], resolved[DEPTH]
 constexpr int SM_TICKETS = 192;     // 2 x ENC_STAGES u32: tile, tile-in-frame
 constexpr int SM_WARP_TOT = 256;    // 32 u32
@@ -538,9 +539,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_RESOLVERS, 3) terse_encode_ker
     TRPX_DYN_SMEM(sm);
     u64* bars = (u64*)(sm + SM_BARS);
     u64* bar_full = bars;
-    u64* bar_ready = bars + ENC_STAGES;
-    u64* bar_packed = bar_ready + ENC_DEPTH;
-    u64* bar_resolved = bar_packed + ENC_DEPTH;
+    u64* bar_resolved = bars + ENC_STAGES;              // (ready / packed are named barriers 2.. and 2+DEPTH..)
     u32* tickets = (u32*)(sm + SM_TICKETS);
     u32* vbases = (u32*)(sm + SM_TICKETS + 32);                         // [ENC_DEPTH] virtual ring offset of a pending tile
     volatile u64* pn64 = (volatile u64*)(sm + SM_MAIL + 32 * ENC_DEPTH);  // [ENC_DEPTH] end position of a resolved tile
@@ -558,8 +557,6 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_RESOLVERS, 3) terse_encode_ker
     if (t == 0) {
         for (int s = 0; s < ENC_STAGES; ++s) mbar_init(&bar_full[s], 1);
         for (int e = 0; e < ENC_DEPTH; ++e) {
-            mbar_init(&bar_ready[e], 1);
-            mbar_init(&bar_packed[e], NT);
             mbar_init(&bar_resolved[e], 1);
         }
         mbar_init_fence();
@@ -571,7 +568,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_RESOLVERS, 3) terse_encode_ker
         // ================================================================ resolver warp r
         for (u32 it = (t - NT) >> 5;; it += ENC_RESOLVERS) {
             const u32 e = it % ENC_DEPTH, use = it / ENC_DEPTH;
-            mbar_wait_sleep(&bar_ready[e], use & 1);       // idle most of the time: do not burn issue slots
+            bar_sync(2 + e, 64);                           // blocks in hardware until worker warp 0 has posted the tile (no spin)
             const u64 tile = mail64[e * 4];
             const u32 tile_bits = mail32[e * 8 + 4];
             if (tile == TILE_END) break;
@@ -579,7 +576,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_RESOLVERS, 3) terse_encode_ker
             const TileGeom g = tile_geom(p, tile);
             const u64 P0 = tile_start(p, tile, g, tile_bits, false);
             const u64 Pn = g.ends ? align_frame(P0 + tile_bits) : P0 + tile_bits;
-            mbar_wait(&bar_packed[e], use & 1);            // the workers' staging stores are visible now
+            bar_sync(2 + ENC_DEPTH + e, NT + 32);          // all workers have packed: their staging stores are visible now
             if (lane == 0) {
                 u32 tout;
                 const u32 tin = tail_handoff(p, tile, stg, tile_bits, P0, Pn, tout);
@@ -727,13 +724,16 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_RESOLVERS, 3) terse_encode_ker
         }
         if (stored) bar_sync(1, NT);                       // E: freed ring words and mailbox entries are reusable
         u32* stg = ring + (vbase & ring_mask) + 1;
-        if (t == 0) {
-            mail64[e * 4] = tile;
-            vbases[e] = vbase;
-            mail32[e * 8 + 4] = tile_bits;
-            mail32[e * 8 + 7] = (vbase & ring_mask) + 1;
-            stg[-1] = 0;
-            mbar_arrive(&bar_ready[e]);                    // the resolver may start its look-back
+        if (warp == 0) {
+            if (lane == 0) {
+                mail64[e * 4] = tile;
+                vbases[e] = vbase;
+                mail32[e * 8 + 4] = tile_bits;
+                mail32[e * 8 + 7] = (vbase & ring_mask) + 1;
+                stg[-1] = 0;
+            }
+            sync_warp();
+            bar_arrive(2 + e, 64);                         // the resolver may start its look-back
         }
         vhead = vbase + need;
         if (it == oldest) vtail = vbase;
@@ -750,7 +750,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_RESOLVERS, 3) terse_encode_ker
                 pack_block12<T>(sk, &w[b * P::BW], sb[b], cnt[b]);
             }
         merge_and_flush(sk, off + len);
-        mbar_arrive(&bar_packed[e]);                       // D: all NT workers arrive -> staging complete
+        bar_arrive(2 + ENC_DEPTH + e, NT + 32);            // D: all NT workers arrive -> staging complete
         // Shared scratch reused by the next iteration is rewritten only after one of its barriers
         // A..C, which no worker passes before all have finished reading this iteration's values.
     }
@@ -758,10 +758,11 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_RESOLVERS, 3) terse_encode_ker
     for (; oldest < it; ++oldest) store_pending(oldest);
     bar_sync(1, NT);
     // tell the resolvers that there is nothing more: the next iteration each of them would serve
-    if (t == 0) {
+    if (warp == 0) {
         for (u32 k = 0; k < (u32)ENC_RESOLVERS; ++k) {
-            mail64[((it + k) % ENC_DEPTH) * 4] = TILE_END;
-            mbar_arrive(&bar_ready[(it + k) % ENC_DEPTH]);
+            if (lane == 0) mail64[((it + k) % ENC_DEPTH) * 4] = TILE_END;
+            sync_warp();
+            bar_arrive(2 + (it + k) % ENC_DEPTH, 64);
         }
     }
     my_max = warp_max(my_max);
