@@ -12,10 +12,9 @@
 #include <string>
 #include <vector>
 
+#include "cli_common.hpp"
 #include <trpx/Grey_tiff_io.hpp>
 #include <trpx/Terse.hpp>
-
-namespace fs = std::filesystem;
 
 template <typename T>
 static std::vector<jpa::tiffio::Image> expand(jpa::Terse& t, std::size_t w, std::size_t h, jpa::tiffio::Kind kind)
@@ -34,69 +33,56 @@ static std::vector<jpa::tiffio::Image> expand(jpa::Terse& t, std::size_t w, std:
 
 int main(int argc, char const* argv[])
 {
-    bool help = false, verbose = false;
-    std::vector<fs::path> params;
-    for (int i = 1; i < argc; ++i) {
-        std::string a = argv[i];
-        if (a == "-help") help = true;
-        else if (a == "-verbose") verbose = true;
-        else params.emplace_back(a);
-    }
-    if (help) {
+    using namespace trpx_cli;
+    const Args args(argc, argv);
+    if (args.help) {
         std::cout << "prolix [-help] [-verbose] [file ...]\n"
                      "  expands all files with the .trpx extension to tiff files with the .tif extension.\n"
                      "\nkeywords:\n  -help     print help\n  -verbose  print expanded filenames and compute times\n";
         return 0;
     }
-    std::chrono::duration<double> user_time(0), io_time(0);
-    std::size_t expanded_files = 0;
-    for (fs::path filename : params) {
-        if (!fs::is_regular_file(filename) || filename.extension() != ".trpx") continue;
-        auto t0 = std::chrono::high_resolution_clock::now();
+    Report rep;
+    for (fs::path const& source : args.files) {
+        if (!fs::is_regular_file(source) || !has_extension(source, {".trpx"})) continue;
+        const auto t_open = Clock::now();
         try {
-            std::ifstream in(filename, std::ios::binary);
-            if (!in.is_open()) { std::cerr << "Failed to open input file " << filename << std::endl; continue; }
-            jpa::Terse trpx(in);
+            std::ifstream in(source, std::ios::binary);
+            if (!in.is_open()) { std::cerr << "Failed to open input file " << source << std::endl; continue; }
+            jpa::Terse packed(in);
             in.close();
-            auto t1 = std::chrono::high_resolution_clock::now();
-            io_time += t1 - t0;
-            std::size_t w, h;
-            if (trpx.dim().size() < 2) w = h = std::size_t(std::sqrt(double(trpx.size())));
-            else { w = trpx.dim()[0]; h = trpx.dim()[1]; }
+            const auto t_gpu = Clock::now();
+            rep.io += t_gpu - t_open;
+            std::size_t w, h;                                          // no dimensions in the header: a square image
+            if (packed.dim().size() < 2) w = h = std::size_t(std::sqrt(double(packed.size())));
+            else { w = packed.dim()[0]; h = packed.dim()[1]; }
             using jpa::tiffio::Kind;
-            std::vector<jpa::tiffio::Image> imgs;
-            if (trpx.bits_per_val() <= 16 && trpx.is_signed()) imgs = expand<std::int16_t>(trpx, w, h, Kind::Int);
-            else if (trpx.bits_per_val() <= 16) imgs = expand<std::uint16_t>(trpx, w, h, Kind::Uint);
-            else if (trpx.bits_per_val() <= 32 && trpx.is_signed()) imgs = expand<std::int32_t>(trpx, w, h, Kind::Int);
-            else if (trpx.bits_per_val() <= 32) imgs = expand<std::uint32_t>(trpx, w, h, Kind::Uint);
-            else {
-                std::cerr << "Terse file " << filename << " encodes data that requires 64 bits per pixel." << std::endl;
+            const unsigned bits = packed.bits_per_val();
+            std::vector<jpa::tiffio::Image> stack;
+            if (bits > 32) {
+                std::cerr << "Terse file " << source << " encodes data that requires 64 bits per pixel." << std::endl;
                 std::cerr << "Prolix cannot process such trpx-stacks." << std::endl;
                 return 0;
             }
-            auto t2 = std::chrono::high_resolution_clock::now();
-            user_time += t2 - t1;
-            fs::path tif = filename;
-            tif.replace_extension(".tif");
-            std::ofstream out(tif, std::ios::binary);
+            if (packed.is_signed()) stack = bits <= 16 ? expand<std::int16_t>(packed, w, h, Kind::Int) : expand<std::int32_t>(packed, w, h, Kind::Int);
+            else stack = bits <= 16 ? expand<std::uint16_t>(packed, w, h, Kind::Uint) : expand<std::uint32_t>(packed, w, h, Kind::Uint);
+            const auto t_write = Clock::now();
+            rep.user += t_write - t_gpu;
+            fs::path target = source;
+            target.replace_extension(".tif");
+            std::ofstream out(target, std::ios::binary);
             if (!out.is_open()) {
-                std::cerr << "Failed to open tif file " << tif << std::endl;
+                std::cerr << "Failed to open tif file " << target << std::endl;
             } else {
-                jpa::tiffio::write(out, imgs);
+                jpa::tiffio::write(out, stack);
                 out.close();
-                fs::remove(filename);
-                ++expanded_files;
+                fs::remove(source);
+                ++rep.done;
             }
-            io_time += std::chrono::high_resolution_clock::now() - t2;
+            rep.io += Clock::now() - t_write;
         } catch (std::exception const& e) {
-            std::cerr << "Error processing " << filename << ": " << e.what() << std::endl;
+            std::cerr << "Error processing " << source << ": " << e.what() << std::endl;
         }
     }
-    if (verbose) {
-        for (fs::path const& f : params) std::cout << "Expanded: " << f << std::endl;
-        std::cout << "Prolix expanded : " << expanded_files << " files\n";
-        std::cout << "User time       : " << user_time.count() << " seconds\n";
-        std::cout << "IO time         : " << io_time.count() << " seconds\n";
-    }
+    if (args.verbose) rep.print("Expanded", "Prolix expanded : ", args);
     return 0;
 }

@@ -10,10 +10,9 @@
 #include <string>
 #include <vector>
 
+#include "cli_common.hpp"
 #include <trpx/Grey_tiff_io.hpp>
 #include <trpx/Terse.hpp>
-
-namespace fs = std::filesystem;
 
 template <typename T>
 static void push_stack(jpa::Terse& t, std::vector<jpa::tiffio::Image> const& imgs)
@@ -36,15 +35,9 @@ static void push_stack_float(jpa::Terse& t, std::vector<jpa::tiffio::Image> cons
 
 int main(int argc, char const* argv[])
 {
-    bool help = false, verbose = false;
-    std::vector<fs::path> params;
-    for (int i = 1; i < argc; ++i) {
-        std::string a = argv[i];
-        if (a == "-help") help = true;
-        else if (a == "-verbose") verbose = true;
-        else params.emplace_back(a);
-    }
-    if (help) {
+    using namespace trpx_cli;
+    const Args args(argc, argv);
+    if (args.help) {
         std::cout << "terse [-help] [-verbose] [file ...]\n"
                      "  compresses all files with .tiff or .tif extensions to terse files with .trpx extensions.\n"
                      "Examples:\n"
@@ -53,62 +46,57 @@ int main(int argc, char const* argv[])
                      "\nkeywords:\n  -help     print help\n  -verbose  print compressed filenames, compute times and compression rate\n";
         return 0;
     }
-    std::chrono::duration<double> user_time(0), io_time(0);
-    double total_trpx = 0, total_tiff = 0;
-    std::size_t compressed_files = 0;
-    for (fs::path const& tif : params) {
-        const std::string ext = tif.extension().string();
-        if (!fs::is_regular_file(tif) || !(ext == ".tiff" || ext == ".tif" || ext == ".TIFF" || ext == ".TIF")) continue;
+    Report rep;
+    double trpx_bytes = 0, tiff_bytes = 0;
+    for (fs::path const& tif : args.files) {
+        if (!fs::is_regular_file(tif) || !has_extension(tif, {".tiff", ".tif", ".TIFF", ".TIF"})) continue;
         try {
-            auto t0 = std::chrono::high_resolution_clock::now();
+            const auto t_open = Clock::now();
             std::ifstream in(tif, std::ios::binary);
             if (!in.is_open()) { std::cerr << "Failed to open input file " << tif << std::endl; continue; }
-            std::vector<jpa::tiffio::Image> imgs = jpa::tiffio::read(in);
+            const std::vector<jpa::tiffio::Image> stack = jpa::tiffio::read(in);
             in.close();
-            if (imgs.empty()) throw std::runtime_error("TIFF file contains no image.");
-            for (auto const& im : imgs) {
-                total_tiff += double(im.data.size());
-                if (im.width != imgs[0].width || im.height != imgs[0].height || im.bits != imgs[0].bits || im.kind != imgs[0].kind)
+            if (stack.empty()) throw std::runtime_error("TIFF file contains no image.");
+            jpa::tiffio::Image const& first = stack.front();
+            for (auto const& im : stack) {
+                tiff_bytes += double(im.data.size());
+                if (im.width != first.width || im.height != first.height || im.bits != first.bits || im.kind != first.kind)
                     throw std::runtime_error("TIFF file contains a stack of images with varying sizes.");
             }
-            auto t1 = std::chrono::high_resolution_clock::now();
-            jpa::Terse compressed;
-            compressed.dim({imgs[0].width, imgs[0].height});          // "width height", as Grey_tif reports it
+            const auto t_gpu = Clock::now();
+            jpa::Terse packed;
+            packed.dim({first.width, first.height});                  // "width height", the order Grey_tif reports
             using jpa::tiffio::Kind;
-            const unsigned b = imgs[0].bits;
-            const Kind k = imgs[0].kind;
-            if (k == Kind::Uint && b == 8) push_stack<std::uint8_t>(compressed, imgs);
-            else if (k == Kind::Uint && b == 16) push_stack<std::uint16_t>(compressed, imgs);
-            else if (k == Kind::Uint && b == 32) push_stack<std::uint32_t>(compressed, imgs);
-            else if (k == Kind::Int && b == 8) push_stack<std::int8_t>(compressed, imgs);
-            else if (k == Kind::Int && b == 16) push_stack<std::int16_t>(compressed, imgs);
-            else if (k == Kind::Int && b == 32) push_stack<std::int32_t>(compressed, imgs);
-            else if (k == Kind::Float && b == 32) push_stack_float<float>(compressed, imgs);
-            else if (k == Kind::Float && b == 64) push_stack_float<double>(compressed, imgs);
-            else throw std::runtime_error("unsupported TIFF pixel type.");
-            total_trpx += double(compressed.terse_size());
-            fs::path trpx = tif;
-            trpx.replace_extension(".trpx");
-            std::ofstream out(trpx, std::ios::binary);
+            switch (first.kind == Kind::Float ? 100 + first.bits : (first.kind == Kind::Int ? 1000 : 0) + first.bits) {
+            case 8: push_stack<std::uint8_t>(packed, stack); break;
+            case 16: push_stack<std::uint16_t>(packed, stack); break;
+            case 32: push_stack<std::uint32_t>(packed, stack); break;
+            case 1008: push_stack<std::int8_t>(packed, stack); break;
+            case 1016: push_stack<std::int16_t>(packed, stack); break;
+            case 1032: push_stack<std::int32_t>(packed, stack); break;
+            case 132: push_stack_float<float>(packed, stack); break;
+            case 164: push_stack_float<double>(packed, stack); break;
+            default: throw std::runtime_error("unsupported TIFF pixel type.");
+            }
+            trpx_bytes += double(packed.terse_size());
+            fs::path target = tif;
+            target.replace_extension(".trpx");
+            std::ofstream out(target, std::ios::binary);
             if (!out.is_open()) throw std::runtime_error("Failed to open trpx file for output.");
-            compressed.write(out);
+            packed.write(out);
             out.close();
             std::cout << "Deleting original TIFF file: " << tif << std::endl;
             fs::remove(tif);
-            ++compressed_files;
-            auto t2 = std::chrono::high_resolution_clock::now();
-            user_time += t2 - t1;
-            io_time += t1 - t0;
+            ++rep.done;
+            rep.user += Clock::now() - t_gpu;
+            rep.io += t_gpu - t_open;
         } catch (std::exception const& e) {
             std::cerr << "Error processing " << tif << ": " << e.what() << std::endl;
         }
     }
-    if (verbose) {
-        for (fs::path const& f : params) std::cout << "Compressed: " << f << std::endl;
-        std::cout << "Terse compressed: " << compressed_files << " files\n";
-        std::cout << "User time       : " << user_time.count() << " seconds\n";
-        std::cout << "IO time         : " << io_time.count() << " seconds\n";
-        if (total_tiff > 0) std::cout << "Compression rate: " << std::round(1000 * (1 - total_trpx / total_tiff)) / 10 << "%\n";
+    if (args.verbose) {
+        rep.print("Compressed", "Terse compressed: ", args);
+        if (tiff_bytes > 0) std::cout << "Compression rate: " << std::round(1000 * (1 - trpx_bytes / tiff_bytes)) / 10 << "%\n";
     }
     return 0;
 }

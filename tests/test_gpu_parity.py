@@ -197,6 +197,29 @@ def test_errors(codec):
     roundtrip(codec, st)
 
 
+def test_garbage_payloads_never_crash(codec):
+    """The reference reads out of bounds on corrupt input (no checks at all); here a corrupt stream may decode to
+    garbage or be flagged TRPX_ERR_MALFORMED, but it must neither fault nor hang, and the context stays usable."""
+    rng = np.random.default_rng(99)
+    n = 512 * 512
+    good = np.stack([orc.synth_frame(orc.U16, 512, 512, 2.0, 50, 300 + f) for f in range(4)])
+    p, fb, pb = codec.encode(good)
+    cases = [rng.integers(0, 256, p.size, dtype=np.uint8),                 # pure noise
+             np.zeros(p.size, np.uint8), np.full(p.size, 0xFF, np.uint8)]  # all-explicit-zero headers / one endless run
+    flipped = p.copy()
+    flipped[rng.integers(0, p.size, 200)] ^= 0x5A                          # a damaged real stream
+    cases.append(flipped)
+    for bad in cases:
+        for sizes in (fb, None):
+            try:
+                d, _ = codec.decode(bad, n, 4, False, np.uint16, frame_bytes=sizes)
+                assert d.shape == (4, n)
+            except trpx_b200.TrpxError as e:
+                assert e.status == trpx_b200.ERR_MALFORMED
+    d, _ = codec.decode(p, n, 4, False, np.uint16, frame_bytes=fb)
+    assert np.array_equal(d, good)
+
+
 # ---------------------------------------------------------------- device-pointer flavour + big shapes
 def test_device_flavour_large_stack_properties(codec):
     """512x512 u16 x 2000 frames resident in HBM: round trip, frame-size bookkeeping, sample frames

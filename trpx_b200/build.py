@@ -57,7 +57,7 @@ def build_host(force=False):
         if not srcs:
             continue
         out = os.path.join(ROOT, "cxx", name)
-        deps = srcs + [os.path.join(ROOT, "include", "trpx", "Terse.hpp"), os.path.join(ROOT, "include", "trpx", "Grey_tiff_io.hpp"),
+        deps = srcs + [os.path.join(ROOT, "include", "trpx", "Terse.hpp"), os.path.join(ROOT, "include", "trpx", "Grey_tiff_io.hpp"), os.path.join(ROOT, "cxx", "cli_common.hpp"),
                        os.path.join(ROOT, "include", "trpx_b200.h"), OUT]
         if force or not os.path.exists(out) or any(os.path.getmtime(out) < os.path.getmtime(d) for d in deps if os.path.exists(d)):
             cmd = [cxx, "-std=c++20", "-O2", "-DNDEBUG", "-Wall", "-I", os.path.join(ROOT, "include")] + srcs + [
