@@ -31,9 +31,9 @@ int emu_encode(const void* px, int dtype, size_t n, size_t frames, unsigned bloc
 extern "C" int emu_decode(const uint8_t* payload, size_t payload_bytes, int is_signed, unsigned block,
                           size_t n, size_t frames, const uint64_t* frame_ends, uint64_t* frame_ends_out,
                           void* out, int out_dtype, uint32_t* status, unsigned seg_bytes,
-                          unsigned warm_bytes, int* used_staged)
+                          unsigned warm_bytes, int* used_staged, unsigned sub_shift)
 {
-    DecPlan pl = dec_plan(out_dtype, payload_bytes, n, frames, block, out, seg_bytes, warm_bytes);
+    DecPlan pl = dec_plan(out_dtype, payload_bytes, n, frames, block, out, seg_bytes, warm_bytes, sub_shift);
     if (!pl.ok) return 1;
     if (used_staged) *used_staged = pl.staged ? 1 : 0;
     void* scratch = aligned_alloc(256, pl.scratch_bytes);

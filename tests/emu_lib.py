@@ -51,14 +51,14 @@ def encode(stack, block=12, incl_stride=0, misalign=0, cap=None):
 
 
 def decode(payload, n, frames, is_signed, out_dtype, block=12, frame_ends=None, seg_bytes=64,
-           warm_bytes=64, misalign_out=0):
+           warm_bytes=64, misalign_out=0, sub_shift=0):
     """Returns (values (frames, n), status, staged, recovered frame ends)."""
     L = lib()
     if not hasattr(L, "_dec_ready"):
         L.emu_decode.restype = C.c_int
         L.emu_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_uint, C.c_size_t, C.c_size_t,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint,
-                                 C.c_uint, C.POINTER(C.c_int)]
+                                 C.c_uint, C.POINTER(C.c_int), C.c_uint]
         L._dec_ready = True
     payload = np.ascontiguousarray(payload, dtype=np.uint8)
     buf = _aligned(payload.size + 16)
@@ -73,6 +73,6 @@ def decode(payload, n, frames, is_signed, out_dtype, block=12, frame_ends=None, 
     fe = None if frame_ends is None else np.ascontiguousarray(frame_ends, dtype=np.uint64)
     rc = L.emu_decode(buf.ctypes.data, payload.size, int(is_signed), block, n, frames,
                       None if fe is None else fe.ctypes.data, fe_out.ctypes.data, outb.ctypes.data,
-                      orc.code_of(npdt), st.ctypes.data, seg_bytes, warm_bytes, C.byref(staged))
+                      orc.code_of(npdt), st.ctypes.data, seg_bytes, warm_bytes, C.byref(staged), sub_shift)
     assert rc == 0
     return outb.view(npdt).reshape(frames, n).copy(), int(st[0]), bool(staged.value), fe_out

@@ -113,3 +113,19 @@ def test_truncated_payload_is_flagged():
     cut = p[: p.size // 2]
     got, status, _, _ = emu_lib.decode(cut, st.shape[1], 1, False, np.uint16, 12, np.array([cut.size], np.uint64))
     assert status == 4
+
+
+@pytest.mark.parametrize("sub_shift", [5, 6, 7, 8])
+def test_checkpoint_spacing_is_a_runtime_choice(sub_shift):
+    """4 / 8 / 16 / 32-byte sub-segments (sparse streams use the small ones: a thread then still owns ~6 blocks)."""
+    rng = np.random.default_rng(17)
+    sparse = (rng.random((3, 12 * 4096 + 4)) < 0.03).astype(np.uint16) * rng.integers(1, 9, size=(3, 12 * 4096 + 4), dtype=np.uint16)
+    n = sparse.shape[1]
+    while (n * 2) % 16:
+        n += 1
+    sparse = np.ascontiguousarray(np.pad(sparse, ((0, 0), (0, n - sparse.shape[1]))))
+    assert roundtrip(sparse, seg_bytes=256, warm_bytes=128, sub_shift=sub_shift) is True
+    dense = np.stack([orc.synth_frame(orc.U16, 128, 96, 2.0, 12, 500 + f) for f in range(2)])
+    assert roundtrip(dense, seg_bytes=512, warm_bytes=256, sub_shift=sub_shift) is True
+    wide = np.stack([orc.kat_fill(orc.U32, 12 * 400, 3 + f) for f in range(2)])
+    assert roundtrip(wide, seg_bytes=1024, warm_bytes=512, sub_shift=sub_shift) is True

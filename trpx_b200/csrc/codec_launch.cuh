@@ -181,7 +181,7 @@ constexpr int SEGTAB_NT = 1024;
 struct DecPlan {
     bool staged;                  // block == 12 and 16-byte aligned frames: fused re-walk + unpack kernel (TMA store)
     u64 nblocks, tiles_per_frame, n_tiles, max_segs;
-    u32 last_cnt, seg_bytes, warm_bytes, subs_per_seg;
+    u32 last_cnt, seg_bytes, warm_bytes, subs_per_seg, sub_shift;
     size_t smem_unpack, off_ckpt, off_hdr_tab, off_segd;
     // scratch layout (byte offsets)
     size_t off_frame_ends, off_seg_base, off_seg_frame, off_seg_entry, off_seg_exit, off_seg_count,
@@ -191,8 +191,9 @@ struct DecPlan {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// sub_shift: log2 of the checkpoint spacing in bits (8 = 32 bytes ... 5 = 4 bytes; 0 = 32 bytes)
 inline DecPlan dec_plan(int out_dtype, u64 payload_bytes, u64 n_values, u64 n_frames, u32 block,
-                        const void* d_out, u32 seg_bytes, u32 warm_bytes)
+                        const void* d_out, u32 seg_bytes, u32 warm_bytes, u32 sub_shift = 0)
 {
     DecPlan pl;
     const size_t so = dtype_size(out_dtype);
@@ -203,8 +204,10 @@ inline DecPlan dec_plan(int out_dtype, u64 payload_bytes, u64 n_values, u64 n_fr
     pl.n_tiles = pl.tiles_per_frame * n_frames;
     if (pl.n_tiles >= (1ull << 31)) pl.ok = false;
     pl.staged = block == 12 && ((uintptr_t)d_out & 15) == 0 && ((n_values * so) & 15) == 0;
+    pl.sub_shift = sub_shift < SUB_SHIFT_MIN || sub_shift > SUB_SHIFT_MAX ? SUB_SHIFT_MAX : sub_shift;
+    const u32 sub_bytes = 1u << (pl.sub_shift - 3);
     pl.seg_bytes = (seg_bytes < SUB_BYTES ? SUB_BYTES : seg_bytes + SUB_BYTES - 1) / SUB_BYTES * SUB_BYTES;
-    pl.subs_per_seg = pl.seg_bytes / SUB_BYTES;
+    pl.subs_per_seg = pl.seg_bytes / sub_bytes;
     pl.warm_bytes = warm_bytes;
     // the walkers keep lane-relative bit positions in 32 bits
     if ((u64)pl.seg_bytes + warm_bytes >= (1ull << 19) || (u64)block * 73 + 12 >= (1ull << 23)) pl.ok = false;
@@ -294,6 +297,7 @@ inline void decode_async(Launcher& L, const void* d_payload, u64 payload_bytes, 
     p.anchors = (u64*)(sc + pl.off_anchors);
     p.ckpt = pl.staged ? (u64*)(sc + pl.off_ckpt) : nullptr;
     p.subs_per_seg = pl.subs_per_seg;
+    p.sub_shift = pl.sub_shift;
     p.hdr_tab = (unsigned short*)(sc + pl.off_hdr_tab);
     p.segd = pl.staged ? (u64*)(sc + pl.off_segd) : nullptr;
     p.tile_blocks = DEC_TB;

@@ -50,6 +50,7 @@ struct DecParams {
     // P1 -> fused P2: exact checkpoints, one per SUB_BYTES of every segment (nullptr on the generic path)
     u64* ckpt;              // [max_segs * subs_per_seg]: first header at or after the sub-segment's first bit
     u32 subs_per_seg;
+    u32 sub_shift;          // log2 of a sub-segment's size in BITS: 8 (32 bytes) for dense streams ... 5 (4 bytes) for sparse ones
     unsigned short* hdr_tab; // [4096] header look-up table in global memory (written by prolix_segments_kernel)
     u64* segd;              // [max_segs * 4] per segment: absolute bit of its start, absolute bit of its frame's end,
                             // index of its first block in the frame, frame | header count << 32 (written by the resolve kernel)
@@ -151,9 +152,10 @@ struct StreamWindow {
     }
 };
 
-// Checkpoint of a 32-byte sub-segment: the first header at or after its first bit, as
+// Checkpoint of a sub-segment (32 bytes of stream for diffraction-like data, down to 4 bytes for sparse data, so
+// that a thread of the unpack kernel always owns about half a dozen blocks): the first header at or after its first bit, as
 // (bit offset from the segment's start : 24 | width carried into that header : 8 | headers of the segment before it : 32).
-constexpr u32 SUB_BYTES = 32, SUB_BITS = SUB_BYTES * 8, SUB_SHIFT = 8;
+constexpr u32 SUB_BYTES = 32, SUB_SHIFT_MAX = 8, SUB_SHIFT_MIN = 5;   // the largest sub-segment (32 bytes) sizes the shared-memory slice
 TRPX_HD u64 pack_ckpt(u32 rel, u32 s, u32 n) { return ((u64)rel << 40) | ((u64)(s & 0xff) << 32) | (u64)n; }
 TRPX_HD u32 ckpt_rel(u64 c) { return (u32)(c >> 40); }
 TRPX_HD u32 ckpt_s(u64 c) { return (u32)(c >> 32) & 0xff; }
@@ -163,39 +165,39 @@ TRPX_HD u32 ckpt_n(u64 c) { return (u32)c; }
 // header's bit offset from the segment's start.
 struct CkptSink {
     u64* row;               // this segment's checkpoints (nullptr: record nothing)
-    u32 subs, next_m;
+    u32 subs, next_m, sh;
     u32 next_rel;           // a header at rel >= next_rel opens a new sub-segment (0xffffffff: never)
-    TRPX_DEVICE void init(u64* row_, u32 subs_)
+    TRPX_DEVICE void init(u64* row_, u32 subs_, u32 sub_shift)
     {
-        row = row_; subs = subs_; next_m = 0;
+        row = row_; subs = subs_; next_m = 0; sh = sub_shift;
         next_rel = row && subs ? 0u : 0xffffffffu;
     }
     TRPX_DEVICE void at(u32 rel, u32 s_prev, u32 n)          // a header starts at rel
     {
         if (rel < next_rel) return;                          // the common case: one compare
-        const u32 m = rel >> SUB_SHIFT;
+        const u32 m = rel >> sh;
         while (next_m <= m && next_m < subs) row[next_m++] = pack_ckpt(rel, s_prev, n);
-        next_rel = next_m < subs ? next_m << SUB_SHIFT : 0xffffffffu;
+        next_rel = next_m < subs ? next_m << sh : 0xffffffffu;
     }
     // The same for the walkers' hot loop, without a divergent branch in the common case (a header opens at
     // most ONE new sub-segment): a predicated 8-byte store and two selects.
     TRPX_DEVICE void at_fast(u32 rel, u32 s_prev, u32 n)
     {
         if (rel < next_rel) return;
-        if ((rel >> SUB_SHIFT) != next_m) { at(rel, s_prev, n); return; }   // skipped sub-segments: rare
+        if ((rel >> sh) != next_m) { at(rel, s_prev, n); return; }   // skipped sub-segments: rare
         row[next_m] = pack_ckpt(rel, s_prev, n);
         ++next_m;
-        next_rel = next_m < subs ? next_m << SUB_SHIFT : 0xffffffffu;
+        next_rel = next_m < subs ? next_m << sh : 0xffffffffu;
     }
     TRPX_DEVICE void run(u32 rel, u32 n, u32 len)            // len one-bit headers (width 0) from rel
     {
         if (rel + len <= next_rel) return;
         at(rel, 0, n);
-        while (next_m < subs && (next_m << SUB_SHIFT) < rel + len) {   // boundaries inside the run are headers themselves
-            const u32 r2 = next_m << SUB_SHIFT;
+        while (next_m < subs && (next_m << sh) < rel + len) {   // boundaries inside the run are headers themselves
+            const u32 r2 = next_m << sh;
             row[next_m++] = pack_ckpt(r2, 0, n + (r2 - rel));
         }
-        next_rel = next_m < subs ? next_m << SUB_SHIFT : 0xffffffffu;
+        next_rel = next_m < subs ? next_m << sh : 0xffffffffu;
     }
     TRPX_DEVICE void finish(u32 rel_exit, u32 s_exit, u32 n)  // sub-segments in which no header starts any more
     {
@@ -452,7 +454,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_walk_kernel(DecParams p)
     }
     NoSink ns;
     CkptSink ck;
-    ck.init(L.have && p.ckpt ? p.ckpt + j * p.subs_per_seg : nullptr, p.subs_per_seg);
+    ck.init(L.have && p.ckpt ? p.ckpt + j * p.subs_per_seg : nullptr, p.subs_per_seg, p.sub_shift);
     warp_walk(p, buf, tab, L, ns, ck);
     if (L.have) {
         if (!L.entered) { L.q_entry = L.q; L.s_entry = L.s; L.n = 0; }   // the warm-up jumped over the whole segment
@@ -496,7 +498,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_resolve_kernel(DecParams p)
             u32 s = state_s(want);
             p.seg_entry[j] = want;
             CkptSink ck;
-            ck.init(p.ckpt ? p.ckpt + j * p.subs_per_seg : nullptr, p.subs_per_seg);
+            ck.init(p.ckpt ? p.ckpt + j * p.subs_per_seg : nullptr, p.subs_per_seg, p.sub_shift);
             const u64 n = walk_headers(p.payload, n_words, g.base_bit, p.block, pos, s, g.r1, ns, &ck, g.r0);
             st_relaxed(&p.seg_exit[j], pack_state(pos, s));
             p.seg_count[j] = n > 0xffffffffull ? 0xffffffffu : (u32)n;
@@ -637,7 +639,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_emit_kernel(DecParams p)
         }
     }
     CkptSink ck;
-    ck.init(nullptr, 0);
+    ck.init(nullptr, 0, SUB_SHIFT_MAX);
     warp_walk(p, buf, tab, L, sink, ck);
     if (L.have) {
         sink.flush();
@@ -960,11 +962,12 @@ TRPX_DEVICE SliceDesc load_slice_desc(const DecParams& p, u32 sl, u32 parts)
     d.c1 = m + 1 < p.subs_per_seg ? row[m + 1] : ~0ull;
     return d;
 }
-TRPX_DEVICE u64 slice_a0(const SliceDesc& d)      // 16-byte aligned byte offset of the slice's first word in the payload
+TRPX_DEVICE u64 slice_a0(const SliceDesc& d, u32 sub_shift)      // 16-byte aligned byte offset of the slice's first word in the payload
 {
-    return ((d.seg_bit + (u64)d.h * UNP_NT * SUB_BITS) >> 3) & ~15ull;
+    return ((d.seg_bit + (((u64)d.h * UNP_NT) << sub_shift)) >> 3) & ~15ull;
 }
-TRPX_DEVICE void fetch_slice(const DecParams& p, u64 a0, uint4 (&pre)[UNP_CHUNKS])
+// (span_chunks: 16-byte pieces of this call's slice: UNP_NT sub-segments + tail)
+TRPX_DEVICE void fetch_slice(const DecParams& p, u64 a0, u32 span_chunks, uint4 (&pre)[UNP_CHUNKS])
 {
     const u64 safe_end = p.payload_bytes & ~15ull;
     const u64 n_words = (p.payload_bytes + 3) >> 2;
@@ -974,7 +977,7 @@ TRPX_DEVICE void fetch_slice(const DecParams& p, u64 a0, uint4 (&pre)[UNP_CHUNKS
         const u32 c = tid() + q * UNP_NT;
         const u64 b = a0 + 16ull * c;
         uint4 v = make_uint4(0, 0, 0, 0);
-        if (c < UNP_SPAN_WORDS / 4) {
+        if (c < span_chunks) {
             if (b + 16 <= safe_end) {
                 v = *(const uint4*)(base + b);
             } else if (b < p.payload_bytes) {
@@ -988,12 +991,12 @@ TRPX_DEVICE void fetch_slice(const DecParams& p, u64 a0, uint4 (&pre)[UNP_CHUNKS
         pre[q] = v;
     }
 }
-TRPX_DEVICE void stage_slice(u32* span, const uint4 (&pre)[UNP_CHUNKS])
+TRPX_DEVICE void stage_slice(u32* span, u32 span_chunks, const uint4 (&pre)[UNP_CHUNKS])
 {
 #pragma unroll
     for (u32 q = 0; q < UNP_CHUNKS; ++q) {
         const u32 c = tid() + q * UNP_NT;
-        if (c < UNP_SPAN_WORDS / 4) {
+        if (c < span_chunks) {
             const u32 i = 4 * c, col = i >> 3, r0 = i & 7;           // 4 words of one column: rows r0 .. r0+3
             const u32 vv[4] = {pre[q].x, pre[q].y, pre[q].z, pre[q].w};
 #pragma unroll
@@ -1028,15 +1031,18 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 3) prolix_unpack_seg_kernel(DecParam
     SliceDesc d0 = load_slice_desc(p, sl, parts), d1 = d0, d2 = d0;
     if (sl + step < total && sl + step >= sl) d1 = load_slice_desc(p, sl + step, parts);
     uint4 pre[UNP_CHUNKS];
-    fetch_slice(p, slice_a0(d0), pre);
+    const u32 sub_shift = p.sub_shift;
+    const u32 span_chunks = (((u32)UNP_NT << (sub_shift - 5)) + UNP_TAIL_WORDS + 4) / 4;   // words of UNP_NT sub-segments + tail
+    const u32 pos_limit = (((u32)UNP_NT << (sub_shift - 3)) + 16) * 8;                    // no header is read past this bit
+    fetch_slice(p, slice_a0(d0, sub_shift), span_chunks, pre);
     for (;;) {
         const bool have1 = sl + step < total && sl + step >= sl;
         const bool have2 = have1 && sl + 2 * step < total && sl + 2 * step >= sl + step;
         if (have2) d2 = load_slice_desc(p, sl + 2 * step, parts);   // arrives during this iteration
-        const u64 a0 = slice_a0(d0);
-        stage_slice(span, pre);                                     // (the previous iteration ended with a barrier)
+        const u64 a0 = slice_a0(d0, sub_shift);
+        stage_slice(span, span_chunks, pre);                                     // (the previous iteration ended with a barrier)
         sync_block();
-        if (have1) fetch_slice(p, slice_a0(d1), pre);               // in flight while this slice is unpacked
+        if (have1) fetch_slice(p, slice_a0(d1, sub_shift), span_chunks, pre);               // in flight while this slice is unpacked
 
         // ---- headers of this CTA: [kA, kB) in segment-local numbering, clipped at the frame's last block
         const u32 kA = d0.rowA != ~0ull ? ckpt_n(d0.rowA) : d0.seg_cnt;
@@ -1082,7 +1088,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 3) prolix_unpack_seg_kernel(DecParam
                     }
                     pos += s * 12;
                     ++k;
-                    if (k < stop_full && pos >= (UNP_NT * SUB_BYTES + 16) * 8) { atomic_max(p.status, DEC_MALFORMED); k = k_end; break; }   // never read a header past the tail
+                    if (k < stop_full && pos >= pos_limit) { atomic_max(p.status, DEC_MALFORMED); k = k_end; break; }   // never read a header past the tail
                 }
                 if (k == k_last && k < k_end && k < c1) {           // the (possibly ragged) last block of the frame
                     u32 hl;

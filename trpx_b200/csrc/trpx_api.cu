@@ -50,6 +50,7 @@ struct trpx_ctx {
     u64 launches = 0;
     std::string last_error;
     std::mutex mu;
+    u32 sub_shift = 0;                   // 0: chosen per call (TRPX_SUB_SHIFT overrides: 5..8)
     u32 seg_bytes = 0, warm_bytes = 0;   // 0: chosen per call from the stream's mean block size (TRPX_SEG_BYTES / TRPX_WARM_BYTES override)
     size_t batch_bytes = 256u << 20;   // raw pixel bytes per pipeline batch of the host flavours
     u32 coop_grid = 0;
@@ -99,19 +100,30 @@ u32 env_u32(const char* name, u32 dflt)
 // < ~700 in 99.9 % of the cases (measured on diffraction, sparse and dark-subtracted frames), whatever the block
 // size; so the warm-up is sized in BLOCKS -- 1200 of the stream's mean block size -- and a segment is at least
 // twice the warm-up.  (A walker that still arrives wrong is re-walked by the resolve kernel: slower, never wrong.)
-void walk_geometry(const trpx_ctx* c, u64 payload_bytes, u64 n_frames, u64 nblocks, u32& seg, u32& warm)
+// Checkpoint spacing: a thread of the unpack kernel owns the blocks whose headers start in one sub-segment; about
+// six blocks per thread keeps its 256-thread slice within one output stage: 32 bytes for diffraction frames
+// (~40 bits per block), down to 4 bytes for sparse counting data (~5 bits per block).
+void walk_geometry(const trpx_ctx* c, u64 payload_bytes, u64 n_frames, u64 nblocks, u32& seg, u32& warm, u32& sub_shift)
 {
     seg = c->seg_bytes;
     warm = c->warm_bytes;
-    if (seg && warm) return;
     const double blocks = (double)n_frames * (double)nblocks;
     const double mean_bits = blocks > 0 ? 8.0 * (double)payload_bytes / blocks : 64.0;
+    sub_shift = c->sub_shift;
+    if (!sub_shift) {
+        sub_shift = SUB_SHIFT_MAX;
+        while (sub_shift > SUB_SHIFT_MIN && (double)(1u << sub_shift) > 9.0 * mean_bits) --sub_shift;
+    }
+    if (seg && warm) return;
     u64 w = (u64)(1200.0 * mean_bits / 8.0);
-    w = (w + 1023) / 1024 * 1024;
-    if (w < 2048) w = 2048;
+    w = (w + 255) / 256 * 256;
+    if (w < 512) w = 512;
     if (w > 131072) w = 131072;
-    u64 sg = (2 * w + 8191) / 8192 * 8192;
-    if (sg < 16384) sg = 16384;
+    // a segment: twice the warm-up, in whole slices of the unpack kernel (256 sub-segments); sparse streams get
+    // short segments in bytes -- the same ~2400 blocks -- and therefore enough walkers to fill the machine
+    const u64 slice = (u64)256 << (sub_shift - 3);
+    u64 sg = (2 * w + slice - 1) / slice * slice;
+    if (sg < slice) sg = slice;
     if (!warm) warm = (u32)w;
     if (!seg) seg = (u32)sg;
 }
@@ -216,6 +228,7 @@ int trpx_ctx_create(int device, trpx_ctx** out)
     }
     c->seg_bytes = env_u32("TRPX_SEG_BYTES", 0);
     c->warm_bytes = env_u32("TRPX_WARM_BYTES", 0);
+    c->sub_shift = env_u32("TRPX_SUB_SHIFT", 0);
     c->batch_bytes = (size_t)env_u32("TRPX_BATCH_MB", (u32)(c->batch_bytes >> 20)) << 20;
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)prolix_resolve_kernel<RESOLVE_NT>, RESOLVE_NT, 0) != cudaSuccess || occ < 1) {
@@ -317,9 +330,9 @@ int trpx_decode_device(trpx_ctx* c, int lane, const uint8_t* d_payload, size_t p
     if (is_signed && !dtype_signed(out_dtype)) return TRPX_ERR_BAD_ARG;      // Terse.hpp:356-357
     if (((uintptr_t)d_payload & 15) || ((uintptr_t)d_out & (dtype_size(out_dtype) - 1))) return TRPX_ERR_BAD_ARG;
     cudaSetDevice(c->device);
-    u32 seg, warm;
-    walk_geometry(c, payload_bytes, n_frames, (n_values + block - 1) / block, seg, warm);
-    DecPlan pl = dec_plan(out_dtype, payload_bytes, n_values, n_frames, block, d_out, seg, warm);
+    u32 seg, warm, sub_shift;
+    walk_geometry(c, payload_bytes, n_frames, (n_values + block - 1) / block, seg, warm, sub_shift);
+    DecPlan pl = dec_plan(out_dtype, payload_bytes, n_values, n_frames, block, d_out, seg, warm, sub_shift);
     if (!pl.ok) return TRPX_ERR_BAD_ARG;
     Lane& l = c->lanes[lane];
     if (!ensure(c, l.dec_scratch, pl.scratch_bytes)) return TRPX_ERR_NOMEM;
@@ -492,9 +505,9 @@ int trpx_decode_host(trpx_ctx* c, const uint8_t* payload, size_t payload_bytes, 
         if (!ensure(c, l.d_in, slab + 32) || !ensure(c, l.d_out, nf * frame_raw + 16) || !ensure(c, l.d_ends, nf * 8) ||
             !ensure_host_ends(c, l, nf)) { rc = TRPX_ERR_NOMEM; break; }
         for (size_t i = 0; i < nf; ++i) l.h_ends[i] = ends[f0 + i] - slab0;
-        u32 seg, warm;
-        walk_geometry(c, slab, nf, (n_values + block - 1) / block, seg, warm);
-        DecPlan pl = dec_plan(out_dtype, slab, n_values, nf, block, l.d_out.p, seg, warm);
+        u32 seg, warm, sub_shift;
+        walk_geometry(c, slab, nf, (n_values + block - 1) / block, seg, warm, sub_shift);
+        DecPlan pl = dec_plan(out_dtype, slab, n_values, nf, block, l.d_out.p, seg, warm, sub_shift);
         if (!pl.ok) { rc = TRPX_ERR_BAD_ARG; break; }
         if (!ensure(c, l.dec_scratch, pl.scratch_bytes)) { rc = TRPX_ERR_NOMEM; break; }
         cudaMemsetAsync((uint8_t*)l.d_in.p + (slab & ~(size_t)15), 0, 32, l.stream);   // defined bytes after the slab
