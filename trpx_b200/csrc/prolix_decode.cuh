@@ -465,6 +465,54 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_walk_kernel(DecParams p)
     }
 }
 
+// Fix-up of ONE segment whose speculative entry was wrong: re-walk it from the exact state (pos, s), but only
+// until the new trajectory meets the one the walker recorded -- a checkpoint that agrees in (position, carried
+// width) proves that both are identical from there on.  A walker that started wrong has locked onto the true
+// chain long before its segment ends, so this costs a few hundred bytes instead of the whole segment: the later
+// checkpoints keep their positions and only get a constant added to their header counts.  Returns false when the
+// trajectories never met (then everything was rewritten and the exit state (pos, s) is new).
+TRPX_DEVICE bool rewalk_until_merged(const DecParams& p, u64 n_words, const SegInfo& g, u64 j, u64& pos, u32& s, u32& count)
+{
+    u64* row = p.ckpt + j * p.subs_per_seg;
+    const u32 subs = p.subs_per_seg, sh = p.sub_shift;
+    StreamWindow sw;
+    sw.init(p.payload, n_words);
+    u32 next_m = 0, n = 0;
+    while (pos < g.r1) {
+        const u64 win = sw.peek(g.base_bit + pos);
+        const u32 rel = (u32)(pos - g.r0);
+        for (const u32 m = rel >> sh; next_m <= m && next_m < subs; ++next_m) {   // this header opens sub-segments next_m .. m
+            const u64 old = row[next_m];
+            if (ckpt_rel(old) == rel && ckpt_s(old) == (s & 0xff)) {
+                const u32 delta = n - ckpt_n(old);
+                if (delta)
+                    for (u32 mm = next_m; mm < subs; ++mm) {
+                        const u64 c = row[mm];
+                        row[mm] = (c & ~0xffffffffull) | (u64)(u32)((u32)c + delta);
+                    }
+                count = p.seg_count[j] + delta;
+                return true;
+            }
+            row[next_m] = pack_ckpt(rel, s, n);
+        }
+        if (s == 0 && (win & 1)) {                            // one-bit headers of empty blocks
+            u64 run = (u64)ffs64(~win | (1ull << 63)) - 1;
+            if (run > g.r1 - pos) run = g.r1 - pos;
+            const u64 bound = g.r0 + ((u64)next_m << sh);     // the next boundary is a header of this run: stop on it
+            if (next_m < subs && pos + run > bound) run = bound - pos;
+            n += (u32)run;
+            pos += run;
+            continue;
+        }
+        const u32 hl = decode_header(win, s);
+        pos += hl + (u64)s * p.block;
+        ++n;
+    }
+    for (; next_m < subs; ++next_m) row[next_m] = pack_ckpt((u32)(pos - g.r0), s, n);
+    count = n;
+    return false;
+}
+
 // ------------------------------------------------------------------ D2: verify / fix until stable, D3: scan
 // Cooperative launch (whole grid resident): grid_sync() is cooperative_groups' grid barrier on the
 // device and a block barrier in the single-CTA emulator run.
@@ -497,11 +545,17 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_resolve_kernel(DecParams p)
             u64 pos = state_pos(want);
             u32 s = state_s(want);
             p.seg_entry[j] = want;
-            CkptSink ck;
-            ck.init(p.ckpt ? p.ckpt + j * p.subs_per_seg : nullptr, p.subs_per_seg, p.sub_shift);
-            const u64 n = walk_headers(p.payload, n_words, g.base_bit, p.block, pos, s, g.r1, ns, &ck, g.r0);
-            st_relaxed(&p.seg_exit[j], pack_state(pos, s));
-            p.seg_count[j] = n > 0xffffffffull ? 0xffffffffu : (u32)n;
+            if (p.ckpt) {                                   // fast path: stop as soon as the recorded trajectory is met
+                u32 count;
+                const bool merged = rewalk_until_merged(p, n_words, g, j, pos, s, count);
+                p.seg_count[j] = count;
+                if (merged) continue;                       // same exit as before: nothing downstream changes
+                st_relaxed(&p.seg_exit[j], pack_state(pos, s));
+            } else {
+                const u64 n = walk_headers(p.payload, n_words, g.base_bit, p.block, pos, s, g.r1, ns);
+                st_relaxed(&p.seg_exit[j], pack_state(pos, s));
+                p.seg_count[j] = n > 0xffffffffull ? 0xffffffffu : (u32)n;
+            }
             atomic_or(flag, 1u);
         }
         grid_sync();
