@@ -1086,6 +1086,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 3) prolix_unpack_seg_kernel(DecParam
     if (sl + step < total && sl + step >= sl) d1 = load_slice_desc(p, sl + step, parts);
     uint4 pre[UNP_CHUNKS];
     const u32 sub_shift = p.sub_shift;
+    const bool sparse = sub_shift < SUB_SHIFT_MAX;
     const u32 span_chunks = (((u32)UNP_NT << (sub_shift - 5)) + UNP_TAIL_WORDS + 4) / 4;   // words of UNP_NT sub-segments + tail
     const u32 pos_limit = (((u32)UNP_NT << (sub_shift - 3)) + 16) * 8;                    // no header is read past this bit
     fetch_slice(p, slice_a0(d0, sub_shift), span_chunks, pre);
@@ -1129,20 +1130,47 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 3) prolix_unpack_seg_kernel(DecParam
                 unsigned char* sbase = stage + phase;
                 // full blocks (12 values) in a tight loop; the frame's ragged last block, if it is mine, afterwards
                 const u32 stop_full = umin3(k_end, c1, k_last);
-                while (k < stop_full) {
-                    u32 hl;
-                    lookup_header(tab, col_bits(colp, pos - cbase), s, hl, s);   // (a header starts < 384 bits into the column)
-                    pos += hl;
-                    O* dst = (O*)(sbase + (k - c0) * (12 * SO));
-                    if (s == 0) {
-#pragma unroll
-                        for (u32 i = 0; i < 12; ++i) dst[i] = (O)0;
-                    } else {
-                        unpack_block12<O, SGN>(span, colp, pos - cbase, pos, s, dst);
+                if (sparse) {
+                    // Sparse streams (checkpoints closer than 32 bytes): the stage starts out all zero (one cooperative
+                    // sweep), so empty blocks cost nothing and a run of their one-bit headers is skipped 32 at a time.
+                    const u32 n16 = (phase + (c1 - c0) * (12 * SO) + 15) >> 4;
+                    uint4* z = (uint4*)stage;
+                    for (u32 i = t; i < n16; i += UNP_NT) z[i] = make_uint4(0, 0, 0, 0);
+                    sync_block();
+                    while (k < stop_full) {
+                        const u32 win = col_bits(colp, pos - cbase);
+                        if (s == 0 && (win & 1)) {
+                            u32 run = (u32)ffs32(~win) - 1;          // ffs32(0) == 0 -> 0xffffffff: all 32 bits set
+                            run = run > 32u ? 32u : run;
+                            run = run > stop_full - k ? stop_full - k : run;
+                            pos += run;
+                            k += run;
+                        } else {
+                            u32 hl;
+                            lookup_header(tab, win, s, hl, s);
+                            pos += hl;
+                            if (s != 0) unpack_block12<O, SGN>(span, colp, pos - cbase, pos, s, (O*)(sbase + (k - c0) * (12 * SO)));
+                            pos += s * 12;
+                            ++k;
+                        }
+                        if (k < stop_full && pos >= pos_limit) { atomic_max(p.status, DEC_MALFORMED); k = k_end; break; }
                     }
-                    pos += s * 12;
-                    ++k;
-                    if (k < stop_full && pos >= pos_limit) { atomic_max(p.status, DEC_MALFORMED); k = k_end; break; }   // never read a header past the tail
+                } else {
+                    while (k < stop_full) {
+                        u32 hl;
+                        lookup_header(tab, col_bits(colp, pos - cbase), s, hl, s);   // (a header starts < 384 bits into the column)
+                        pos += hl;
+                        O* dst = (O*)(sbase + (k - c0) * (12 * SO));
+                        if (s == 0) {
+#pragma unroll
+                            for (u32 i = 0; i < 12; ++i) dst[i] = (O)0;
+                        } else {
+                            unpack_block12<O, SGN>(span, colp, pos - cbase, pos, s, dst);
+                        }
+                        pos += s * 12;
+                        ++k;
+                        if (k < stop_full && pos >= pos_limit) { atomic_max(p.status, DEC_MALFORMED); k = k_end; break; }   // never read a header past the tail
+                    }
                 }
                 if (k == k_last && k < k_end && k < c1) {           // the (possibly ragged) last block of the frame
                     u32 hl;
