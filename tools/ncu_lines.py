@@ -23,6 +23,11 @@ def main():
     if "--by-inst" in sys.argv:
         sys.argv.remove("--by-inst")
         SORT = 0
+    dump = None                       # --sass FILE:LINE[,LINE...] | all : list the SASS of those lines with their counts
+    if "--sass" in sys.argv:
+        i = sys.argv.index("--sass")
+        dump = sys.argv[i + 1]
+        del sys.argv[i:i + 2]
     rep, kre, cubin, mangled = sys.argv[1:5]
     top = int(sys.argv[5]) if len(sys.argv) > 5 else 40
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre],
@@ -61,6 +66,14 @@ def main():
             line_of.append(curline)
     if len(line_of) != len(sass):
         print("warning: %d SASS rows in the report vs %d in nvdisasm" % (len(sass), len(line_of)))
+    if dump:
+        want = None if dump == "all" else set(int(x) for x in dump.split(","))
+        for i, r in enumerate(sass):
+            key = line_of[i] if i < len(line_of) else ("?", 0)
+            if want is None or key[1] in want:
+                print("%5d %-24s %10s %6s  %s" % (i, "%s:%d" % key, r[ci["Instructions Executed"]],
+                                                  r[ci["Warp Stall Sampling (All Samples)"]], r[ci["Source"]][:90]))
+        return
     agg = defaultdict(lambda: [0, 0, 0])
     tot = [0, 0, 0]
     for i, r in enumerate(sass):

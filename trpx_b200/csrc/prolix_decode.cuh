@@ -250,7 +250,7 @@ TRPX_DEVICE u64 walk_headers(const u32* payload, u64 n_words, u64 base_bit, u32 
 // drops them into a [word][lane] table with a 33-word pitch, so that every LDS of a walk step is
 // bank-conflict free however far apart the lanes' positions are.  A round advances 28 words; the
 // 4-word overlap lets a header that starts in word 30 still see its 12 bits.
-constexpr u32 WALK_PITCH = 33;
+constexpr u32 WALK_PITCH = 32;
 constexpr u32 WALK_ROUND_WORDS = 32, WALK_ROUND_STRIDE = 28;
 constexpr u32 WALK_BUF_WORDS = WALK_PITCH * WALK_ROUND_WORDS;
 
@@ -920,69 +920,97 @@ struct SmemBits {                                        // sequential reader ov
     }
 };
 
-// 32 stream bits starting `rel` bits into the thread's column (rows 0..19: rel + 32 <= 640)
-TRPX_DEVICE u32 col_bits(const u32* colp, u32 rel)
+// 32 stream bits starting `rel` bits into the thread's column (rows 0..19: rel + 32 <= 640).  col_a is the
+// shared-window address of the column's row 0: shift, multiply-add, two loads, one funnel shift (which takes
+// rel mod 32 by itself).
+TRPX_DEVICE u32 col_window(saddr_t col_a, u32 rel)
 {
-    const u32* w = colp + (rel >> 5) * UNP_CP;
-    return funnel_r(w[0], w[UNP_CP], rel & 31);
+    const saddr_t a = col_a + (rel >> 5) * (UNP_CP * 4);
+    return funnel_r(lds_u32(a), lds_u32_at<UNP_CP * 4>(a), rel);
+}
+TRPX_DEVICE void lookup_header_s(saddr_t tab_a, u32 win, u32 s, u32& hl, u32& s_new)
+{
+    const u32 e = lds_u16(tab_a + ((win & (HDR_TAB_ENTRIES - 1)) << 1));
+    hl = e & 15;
+    s_new = (e & HDR_SAME) ? s : e >> 8;
 }
 
 template <typename O> struct UnpCap { static constexpr u32 BLOCKS = UNP_STAGE_BYTES / (12 * sizeof(O)); };
 
+template <u32 SO>
+TRPX_DEVICE void sts_zero_block(saddr_t d)                // 12 values of SO bytes, aligned as the stores below
+{
+    if (SO == 1) { sts_u32(d, 0); sts_u32(d + 4, 0); sts_u32(d + 8, 0); }
+    else if (SO == 2) { sts_v2(d, 0, 0); sts_v2(d + 8, 0, 0); sts_v2(d + 16, 0, 0); }
+    else
+#pragma unroll
+        for (u32 i = 0; i < 12 * SO; i += 16) sts_v4(d + i, 0, 0, 0, 0);
+}
+
 // One full block (12 values of width s >= 1 starting at bit `pos`) -> dst (aligned for the vector
-// stores used below).  Every field group is fetched straight from its own bit position: twelve
-// independent extractions, no serial bit-reader state.
+// stores used below).  Every field group is fetched straight from its own bit position: independent
+// extractions, no serial bit-reader state.
 template <typename O, bool SGN>
-TRPX_DEVICE void unpack_block12(const u32* sp, const u32* colp, u32 rel, u32 pos, u32 s, O* dst)
+TRPX_DEVICE void unpack_block12(const u32* sp, saddr_t col_a, u32 rel, u32 pos, u32 s, saddr_t dst_a)
 {
     constexpr u32 SO = sizeof(O);
     const bool in_rows = rel + 12 * s + 32 <= UNP_ROWS * 32;      // the whole block is inside the column's 20 rows
     if (SO == 2 && s <= 16 && in_rows) {
         // two fields of s bits -> two 16-bit lanes with one multiply-add (the encoder's trick reversed)
-        const u32 m2 = s == 16 ? 0xffffffffu : (1u << (2 * s)) - 1;
+        const u32 m2 = low_mask(2 * s);
         const u32 K = 65536u - (1u << s);
-        const u32 KS = (0xffffu << s) & 0xffffu;          // sign extension of a 16-bit lane
         u32 o[6];
+        if (s <= 8) {                                     // a 32-bit window holds four fields: three windows per block
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            const u32 pm = col_bits(colp, rel + 2 * s * i) & m2;
-            u32 x = pm + (pm >> s) * K;
-            if (SGN) x |= ((x >> (s - 1)) & 0x00010001u) * KS;
-            o[i] = x;
+            for (int i = 0; i < 3; ++i) {
+                const u32 q = col_window(col_a, rel + 4 * s * i);
+                const u32 p0 = q & m2, p1 = (q >> (2 * s)) & m2;
+                o[2 * i] = p0 + (p0 >> s) * K;
+                o[2 * i + 1] = p1 + (p1 >> s) * K;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const u32 pm = col_window(col_a, rel + 2 * s * i) & m2;
+                o[i] = pm + (pm >> s) * K;
+            }
         }
-        uint2* d = (uint2*)dst;
-        d[0] = make_uint2(o[0], o[1]); d[1] = make_uint2(o[2], o[3]); d[2] = make_uint2(o[4], o[5]);
+        if (SGN) {
+            const u32 KS = (0xffffu << s) & 0xffffu;      // sign extension of a 16-bit lane
+#pragma unroll
+            for (int i = 0; i < 6; ++i) o[i] |= ((o[i] >> (s - 1)) & 0x00010001u) * KS;
+        }
+        sts_v2(dst_a, o[0], o[1]); sts_v2(dst_a + 8, o[2], o[3]); sts_v2(dst_a + 16, o[4], o[5]);
         return;
     }
     if (SO == 1 && s <= 8 && in_rows) {
-        const u32 m4 = s == 8 ? 0xffffffffu : (1u << (4 * s)) - 1;
+        const u32 m4 = low_mask(4 * s);
         const u32 m2 = (1u << (2 * s)) - 1;
         const u32 K8 = 256u - (1u << s);
         const u32 KS = (0xffu << s) & 0xffu;
-        u32* d = (u32*)dst;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            const u32 q = col_bits(colp, rel + 4 * s * i) & m4;
+            const u32 q = col_window(col_a, rel + 4 * s * i) & m4;
             const u32 p0 = q & m2, p1 = s == 8 ? (q >> 16) : (q >> (2 * s));
             u32 x = (p0 + (p0 >> s) * K8) | ((p1 + (p1 >> s) * K8) << 16);
             if (SGN) x |= ((x >> (s - 1)) & 0x01010101u) * KS;
-            d[i] = x;
+            sts_u32(dst_a + 4 * i, x);
         }
         return;
     }
     if (SO == 4 && s <= 32 && in_rows) {
-        const u32 m = s == 32 ? 0xffffffffu : (1u << s) - 1;
+        const u32 m = low_mask(s);
         u32 o[12];
 #pragma unroll
         for (int i = 0; i < 12; ++i) {
-            u32 v = col_bits(colp, rel + s * i) & m;
+            u32 v = col_window(col_a, rel + s * i) & m;
             if (SGN && s < 32 && ((v >> (s - 1)) & 1)) v |= ~0u << s;
             o[i] = v;
         }
-        uint4* d = (uint4*)dst;
-        d[0] = make_uint4(o[0], o[1], o[2], o[3]); d[1] = make_uint4(o[4], o[5], o[6], o[7]); d[2] = make_uint4(o[8], o[9], o[10], o[11]);
+        sts_v4(dst_a, o[0], o[1], o[2], o[3]); sts_v4(dst_a + 16, o[4], o[5], o[6], o[7]); sts_v4(dst_a + 32, o[8], o[9], o[10], o[11]);
         return;
     }
+    O* dst = (O*)saddr_to_ptr(dst_a);
     SmemBits br;
     br.init(sp, pos);
     for (u32 i = 0; i < 12; ++i) dst[i] = convert_value<O, SGN>(s <= 32 ? (u64)br.get(s) : br.get_wide(s), s);
@@ -1073,6 +1101,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 3) prolix_unpack_seg_kernel(DecParam
     unsigned short* tab = (unsigned short*)(sm + UNP_SM_TAB);
     u32* span = (u32*)(sm + UNP_SM_SPAN);
     unsigned char* stage = sm + UNP_SM_STAGE;
+    const saddr_t tab_a = saddr(tab), span_a = saddr(span), stage_a = saddr(stage);
     const u32 t = tid();
     const u32 parts = (p.subs_per_seg + UNP_NT - 1) / UNP_NT;       // slices per segment
     const u64 total64 = p.max_segs * parts;
@@ -1116,7 +1145,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 3) prolix_unpack_seg_kernel(DecParam
                 cbase = pos & ~255u;                                 // first bit of the column my first header is in
             }
             const u32 k_begin = k;
-            const u32* colp = span + (cbase >> 8);
+            const saddr_t col_a = span_a + (cbase >> 8) * 4;         // my column's row 0
             const u64 b0 = d0.b0;
             const u32 k_last = p.nblocks - 1 - b0 < 0xffffffffull ? (u32)(p.nblocks - 1 - b0) : 0xffffffffu;   // the frame's (possibly ragged) last block
             const u32 frame_end_pos = (u32)((d0.frame_end_bit - a0 * 8 < 0xffffffffull) ? d0.frame_end_bit - a0 * 8 : 0xffffffffull);
@@ -1130,6 +1159,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 3) prolix_unpack_seg_kernel(DecParam
                 unsigned char* sbase = stage + phase;
                 // full blocks (12 values) in a tight loop; the frame's ragged last block, if it is mine, afterwards
                 const u32 stop_full = umin3(k_end, c1, k_last);
+                saddr_t dst_a = stage_a + phase + (k - c0) * (12 * SO);   // (only used while k is inside the chunk)
                 if (sparse) {
                     // Sparse streams (checkpoints closer than 32 bytes): the stage starts out all zero (one cooperative
                     // sweep), so empty blocks cost nothing and a run of their one-bit headers is skipped 32 at a time.
@@ -1138,43 +1168,41 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 3) prolix_unpack_seg_kernel(DecParam
                     for (u32 i = t; i < n16; i += UNP_NT) z[i] = make_uint4(0, 0, 0, 0);
                     sync_block();
                     while (k < stop_full) {
-                        const u32 win = col_bits(colp, pos - cbase);
+                        const u32 win = col_window(col_a, pos - cbase);
                         if (s == 0 && (win & 1)) {
                             u32 run = (u32)ffs32(~win) - 1;          // ffs32(0) == 0 -> 0xffffffff: all 32 bits set
                             run = run > 32u ? 32u : run;
                             run = run > stop_full - k ? stop_full - k : run;
                             pos += run;
                             k += run;
+                            dst_a += run * (12 * SO);
                         } else {
                             u32 hl;
-                            lookup_header(tab, win, s, hl, s);
+                            lookup_header_s(tab_a, win, s, hl, s);
                             pos += hl;
-                            if (s != 0) unpack_block12<O, SGN>(span, colp, pos - cbase, pos, s, (O*)(sbase + (k - c0) * (12 * SO)));
+                            if (s != 0) unpack_block12<O, SGN>(span, col_a, pos - cbase, pos, s, dst_a);
                             pos += s * 12;
                             ++k;
+                            dst_a += 12 * SO;
                         }
                         if (k < stop_full && pos >= pos_limit) { atomic_max(p.status, DEC_MALFORMED); k = k_end; break; }
                     }
                 } else {
                     while (k < stop_full) {
                         u32 hl;
-                        lookup_header(tab, col_bits(colp, pos - cbase), s, hl, s);   // (a header starts < 384 bits into the column)
+                        lookup_header_s(tab_a, col_window(col_a, pos - cbase), s, hl, s);   // (a header starts < 384 bits into the column)
                         pos += hl;
-                        O* dst = (O*)(sbase + (k - c0) * (12 * SO));
-                        if (s == 0) {
-#pragma unroll
-                            for (u32 i = 0; i < 12; ++i) dst[i] = (O)0;
-                        } else {
-                            unpack_block12<O, SGN>(span, colp, pos - cbase, pos, s, dst);
-                        }
+                        if (s == 0) sts_zero_block<SO>(dst_a);
+                        else unpack_block12<O, SGN>(span, col_a, pos - cbase, pos, s, dst_a);
                         pos += s * 12;
                         ++k;
+                        dst_a += 12 * SO;
                         if (k < stop_full && pos >= pos_limit) { atomic_max(p.status, DEC_MALFORMED); k = k_end; break; }   // never read a header past the tail
                     }
                 }
                 if (k == k_last && k < k_end && k < c1) {           // the (possibly ragged) last block of the frame
                     u32 hl;
-                    lookup_header(tab, col_bits(colp, pos - cbase), s, hl, s);
+                    lookup_header_s(tab_a, col_window(col_a, pos - cbase), s, hl, s);
                     pos += hl;
                     O* dst = (O*)(sbase + (k - c0) * (12 * SO));
                     SmemBits br;

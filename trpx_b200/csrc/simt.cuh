@@ -104,6 +104,49 @@ TRPX_DEVICE void st_stream(uint4* p, uint4 v) { __stcs(p, v); }
 
 TRPX_DEVICE u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
 
+// ---- shared memory through 32-bit shared-window addresses ----
+// The hot inner loops of the decoder address shared memory with ONE register per base (no generic-pointer
+// arithmetic, no re-derivation of the window base): saddr() converts once, the accessors below take
+// base + byte offset.  Loads are volatile asm (kept in program order with barriers) without a memory clobber.
+typedef u32 saddr_t;
+TRPX_DEVICE saddr_t saddr(const void* p) { return smem_addr(p); }
+TRPX_DEVICE void* saddr_to_ptr(saddr_t a) { return __cvta_shared_to_generic((size_t)a); }
+TRPX_DEVICE u32 lds_u32(saddr_t a)
+{
+    u32 v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+template <int OFF>
+TRPX_DEVICE u32 lds_u32_at(saddr_t a)                    // [a + OFF], OFF folded into the instruction
+{
+    u32 v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF));
+    return v;
+}
+TRPX_DEVICE u32 lds_u16(saddr_t a)
+{
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+TRPX_DEVICE void sts_u32(saddr_t a, u32 x) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(x) : "memory"); }
+TRPX_DEVICE void sts_v2(saddr_t a, u32 x, u32 y)
+{
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+TRPX_DEVICE void sts_v4(saddr_t a, u32 x, u32 y, u32 z, u32 w)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+// the low n bits set, n clamped to 32 (one BMSK instead of shift / not / select)
+TRPX_DEVICE u32 low_mask(u32 n)
+{
+    u32 m;
+    asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(m) : "r"(0u), "r"(n));
+    return m;
+}
+
 // ---- mbarrier (shared::cta) ----
 TRPX_DEVICE void mbar_init(u64* bar, u32 count)
 {
@@ -289,6 +332,22 @@ inline u32 atomic_max(u32* p, u32 v) { u32 o = *p; if (v > o) *p = v; return o; 
 inline u64 ld_relaxed(const u64* p) { return *(const volatile u64*)p; }
 inline void st_relaxed(u64* p, u64 v) { *(volatile u64*)p = v; }
 inline u32 ld_relaxed(const u32* p) { return *(const volatile u32*)p; }
+// shared-window addresses: byte offsets into the block's dynamic shared memory (bounds-checked here)
+typedef u32 saddr_t;
+inline saddr_t saddr(const void* p) { return (u32)((const unsigned char*)p - ::emu::dyn_smem()); }
+inline unsigned char* saddr_ptr(saddr_t a, u32 n)
+{
+    if ((size_t)a + n > 232448u || (a % n) != 0) ::emu::trap();
+    return ::emu::dyn_smem() + a;
+}
+inline void* saddr_to_ptr(saddr_t a) { return ::emu::dyn_smem() + a; }
+inline u32 lds_u32(saddr_t a) { return *(const u32*)saddr_ptr(a, 4); }
+template <int OFF> inline u32 lds_u32_at(saddr_t a) { return *(const u32*)saddr_ptr(a + (u32)OFF, 4); }
+inline u32 lds_u16(saddr_t a) { return *(const unsigned short*)saddr_ptr(a, 2); }
+inline void sts_u32(saddr_t a, u32 x) { *(u32*)saddr_ptr(a, 4) = x; }
+inline void sts_v2(saddr_t a, u32 x, u32 y) { u32* d = (u32*)saddr_ptr(a, 8); d[0] = x; d[1] = y; }
+inline void sts_v4(saddr_t a, u32 x, u32 y, u32 z, u32 w) { u32* d = (u32*)saddr_ptr(a, 16); d[0] = x; d[1] = y; d[2] = z; d[3] = w; }
+inline u32 low_mask(u32 n) { return n >= 32 ? 0xffffffffu : (1u << n) - 1; }
 inline u32 ld_stream(const u32* p) { return *p; }
 inline void st_stream(u32* p, u32 v) { *p = v; }
 inline void st_stream(uint4* p, uint4 v) { *p = v; }
