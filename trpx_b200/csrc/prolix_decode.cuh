@@ -1124,7 +1124,8 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 3) prolix_unpack_seg_kernel(DecParam
         const bool have2 = have1 && sl + 2 * step < total && sl + 2 * step >= sl + step;
         if (have2) d2 = load_slice_desc(p, sl + 2 * step, parts);   // arrives during this iteration
         const u64 a0 = slice_a0(d0, sub_shift);
-        stage_slice(span, span_chunks, pre);                                     // (the previous iteration ended with a barrier)
+        stage_slice(span, span_chunks, pre);          // (nobody reads the span any more: every thread is past the barrier that followed the unpack loop)
+        if (t == 0) bulk_wait_read0();                // the previous slice's bulk store has finished reading the output stage
         sync_block();
         if (have1) fetch_slice(p, slice_a0(d1, sub_shift), span_chunks, pre);               // in flight while this slice is unpacked
 
@@ -1224,20 +1225,21 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 3) prolix_unpack_seg_kernel(DecParam
                 for (u32 i = t; i < head; i += UNP_NT) gdst[i] = sbase[i];
                 for (u32 i = head + mid + t; i < bytes; i += UNP_NT) gdst[i] = sbase[i];
                 if (t == 0 && mid) {
-                    bulk_s2g(gdst + head, sbase + head, mid);
+                    bulk_s2g(gdst + head, sbase + head, mid);       // drains while the next slice is staged
                     bulk_commit();
-                    bulk_wait_read0();
                 }
-                sync_block();
+                if (c0 + CB < kB) {                                 // another chunk of this slice reuses the stage
+                    if (t == 0) bulk_wait_read0();
+                    sync_block();
+                }
             }
-        } else {
-            sync_block();                                           // everybody has staged before the span is overwritten
         }
         if (!have1) break;
         sl += step;
         d0 = d1;
         d1 = d2;
     }
+    if (t == 0) bulk_wait_read0();                                  // shared memory must outlive the last bulk store
 }
 
 // ------------------------------------------------------------------ frame sizes unknown
