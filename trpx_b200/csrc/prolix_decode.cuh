@@ -172,6 +172,7 @@ struct CkptSink {
         row = row_; subs = subs_; next_m = 0; sh = sub_shift;
         next_rel = row && subs ? 0u : 0xffffffffu;
     }
+    TRPX_DEVICE void sync_rel() { next_rel = row && next_m < subs ? next_m << sh : 0xffffffffu; }   // after next_m was moved by hand
     TRPX_DEVICE void at(u32 rel, u32 s_prev, u32 n)          // a header starts at rel
     {
         if (rel < next_rel) return;                          // the common case: one compare
@@ -247,9 +248,9 @@ TRPX_DEVICE u64 walk_headers(const u32* payload, u64 n_words, u64 base_bit, u32 
 // walkers below are the production path: 32 independent walks per warp (one per lane), the stream
 // staged through shared memory in rounds.  Each lane fetches ITS OWN next 128 bytes with eight 16-byte
 // loads (all in flight while the current round is walked: the prefetch lives in registers), then
-// drops them into a [word][lane] table with a 33-word pitch, so that every LDS of a walk step is
-// bank-conflict free however far apart the lanes' positions are.  A round advances 28 words; the
-// 4-word overlap lets a header that starts in word 30 still see its 12 bits.
+// drops them into a [word][lane] table (pitch 32: a lane's words all live in bank `lane`), so that every
+// LDS / STS of a walk step is bank-conflict free however far apart the lanes' positions are.  A round
+// advances 28 words; the 4-word overlap lets a header that starts in word 30 still see its 12 bits.
 constexpr u32 WALK_PITCH = 32;
 constexpr u32 WALK_ROUND_WORDS = 32, WALK_ROUND_STRIDE = 28;
 constexpr u32 WALK_BUF_WORDS = WALK_PITCH * WALK_ROUND_WORDS;
@@ -362,6 +363,80 @@ TRPX_DEVICE void warp_walk(const DecParams& p, u32* buf, const unsigned short* t
     }
 }
 
+// The walk kernel's own loop: the steps of warp_walk with no sink, the checkpoint bookkeeping inlined (one
+// compare per step against the stream position of the next sub-segment boundary; the store and the advance
+// predicated), shared memory through window addresses, and the block size folded in when it is 12.
+template <bool B12>
+TRPX_DEVICE void warp_walk_ckpt(const DecParams& p, u32* buf, const unsigned short* tab, WalkLane& L, CkptSink& ck)
+{
+    const u32 lane = tid() & 31;
+    if (!L.have) { L.qB = 0; L.q = 0xffffffffu; }
+    const u32 my_rounds = L.have ? ((L.qB + 31) >> 5) / WALK_ROUND_STRIDE + 1 : 0u;
+    const u32 first_round = L.have ? (L.q >> 5) / WALK_ROUND_STRIDE : 0xffffffffu;
+    u32 r = warp_min_u32(first_round);
+    const u32 r_end = warp_max(my_rounds);
+    if (r >= r_end) return;
+    const u32 blk = B12 ? 12u : p.block;
+    const saddr_t tab_a = saddr(tab);
+    const saddr_t lane_a = saddr(buf) + lane * 4;
+    const u32 sub = 1u << ck.sh;
+    u32 q_event = L.entered ? 0xffffffffu : L.qA;           // the segment's first bit (afterwards only runs of empty blocks are special)
+    u32 q_ck = 0xffffffffu;                                 // position of the next sub-segment boundary; armed on entry
+    uint4 pre[8];
+    walk_fetch(p, L, r, pre);
+    for (; r < r_end; ++r) {
+        sync_warp();                                        // everybody is done reading the previous round
+        walk_stage(buf, pre);
+        sync_warp();
+        if (r + 1 < r_end) walk_fetch(p, L, r + 1, pre);    // in flight while this round is walked
+        const u32 w0 = r * WALK_ROUND_STRIDE;
+        const u32 q_round = (w0 + 31) << 5;                 // headers below this bit are readable in this round
+        const u32 qlim = L.qB < q_round ? L.qB : q_round;
+        const saddr_t col_a = lane_a - w0 * (WALK_PITCH * 4);
+        for (;;) {
+            if (!any_lane(L.q < qlim)) break;
+#pragma unroll
+            for (int rep = 0; rep < 2; ++rep) {             // two steps per vote
+                if (L.q < qlim) {
+                    const saddr_t a = col_a + (L.q >> 5) * (WALK_PITCH * 4);
+                    const u32 win = funnel_r(lds_u32(a), lds_u32_at<WALK_PITCH * 4>(a), L.q);
+                    const bool isrun = L.s == 0 && (win & 1);
+                    if (L.q >= q_event || isrun) {          // ---- rare: entering the segment, runs of empty blocks
+                        if (!L.entered && L.q >= L.qA) { L.entered = true; L.q_entry = L.q; L.s_entry = L.s; L.n = 0; }
+                        if (L.entered) ck.sync_rel();
+                        if (isrun) {                        // a run of '1' headers of empty blocks, 1 bit each
+                            const u32 stop = L.entered ? L.qB : L.qA;
+                            u32 run = (u32)ffs32(~win) - 1; // ffs32(0) == 0 -> 0xffffffff: all 32 bits set
+                            run = run > 32u ? 32u : run;
+                            run = run > stop - L.q ? stop - L.q : run;
+                            if (L.entered) ck.run(L.q - L.qA, L.n, run);
+                            L.q += run;
+                            L.n += run;
+                        }
+                        q_event = L.entered ? 0xffffffffu : L.qA;
+                        q_ck = L.entered && ck.next_rel != 0xffffffffu ? L.qA + ck.next_rel : 0xffffffffu;
+                        if (isrun) continue;
+                    }
+                    const u32 e = lds_u16(tab_a + ((win & (HDR_TAB_ENTRIES - 1)) << 1));
+                    const u32 s_new = (e & HDR_SAME) ? L.s : e >> 8;
+                    if (L.q >= q_ck) {                      // this header opens sub-segment next_m (and, rarely, more than one)
+                        const u32 rel = L.q - L.qA;
+                        do {
+                            ck.row[ck.next_m] = pack_ckpt(rel, L.s, L.n);
+                            ++ck.next_m;
+                            q_ck = ck.next_m < ck.subs ? q_ck + sub : 0xffffffffu;
+                        } while (L.q >= q_ck);
+                    }
+                    L.q += (e & 15) + s_new * blk;
+                    L.n += 1;
+                    L.s = s_new;
+                }
+            }
+        }
+    }
+    if (L.entered) ck.sync_rel();
+}
+
 // ------------------------------------------------------------------ D0: segment table
 // nseg(f) = ceil(bytes_f / seg_bytes); seg_base = exclusive scan; seg_frame[j] = f.  One CTA.
 template <int NT>
@@ -452,10 +527,10 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_walk_kernel(DecParams p)
         L.qA = (u32)(g.r0 - delta);
         L.qB = (u32)(g.r1 - delta);
     }
-    NoSink ns;
     CkptSink ck;
     ck.init(L.have && p.ckpt ? p.ckpt + j * p.subs_per_seg : nullptr, p.subs_per_seg, p.sub_shift);
-    warp_walk(p, buf, tab, L, ns, ck);
+    if (p.block == 12) warp_walk_ckpt<true>(p, buf, tab, L, ck);
+    else warp_walk_ckpt<false>(p, buf, tab, L, ck);
     if (L.have) {
         if (!L.entered) { L.q_entry = L.q; L.s_entry = L.s; L.n = 0; }   // the warm-up jumped over the whole segment
         ck.finish(L.q - L.qA, L.s, (u32)L.n);
