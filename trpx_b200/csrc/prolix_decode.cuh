@@ -269,15 +269,16 @@ struct WalkLane {
 TRPX_DEVICE void walk_fetch(const DecParams& p, const WalkLane& L, u32 round, uint4 (&pre)[8])
 {
     const u64 byte0 = L.cb + (u64)round * (WALK_ROUND_STRIDE * 4);
+    const bool want = L.have && (round + 1) * (WALK_ROUND_STRIDE * 32) + 128 > L.q;   // (rounds that end before the lane's position: nothing to read)
     const u64 safe_end = p.payload_bytes & ~15ull;          // 16-byte loads stay inside the payload buffer
     const unsigned char* base = (const unsigned char*)p.payload;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const u64 b = byte0 + 16u * k;
         uint4 v = make_uint4(0, 0, 0, 0);
-        if (L.have && b + 16 <= safe_end) {
+        if (want && b + 16 <= safe_end) {
             v = *(const uint4*)(base + b);
-        } else if (L.have && b < p.payload_bytes) {          // ragged end: word by word, zero beyond
+        } else if (want && b < p.payload_bytes) {            // ragged end: word by word, zero beyond
             const u64 n_words = (p.payload_bytes + 3) >> 2;
             const u64 wi = b >> 2;
             v.x = wi < n_words ? p.payload[wi] : 0u;
@@ -363,14 +364,16 @@ TRPX_DEVICE void warp_walk(const DecParams& p, u32* buf, const unsigned short* t
     }
 }
 
-// The walk kernel's own loop: the steps of warp_walk with no sink, the checkpoint bookkeeping inlined (one
-// compare per step against the stream position of the next sub-segment boundary; the store and the advance
-// predicated), shared memory through window addresses, and the block size folded in when it is 12.
+// The walk kernel's own loop: the steps of warp_walk with no sink, in two phases per round.  Phase A is the
+// speculative warm-up (all lanes of a warp start it together and leave it within a round of each other): nothing
+// but window -> table -> advance.  Phase B walks the segment proper: header count, and the checkpoint bookkeeping
+// inlined (one compare per step against the stream position of the next sub-segment boundary).  Shared memory
+// through window addresses; the block size folded in when it is 12.
 template <bool B12>
 TRPX_DEVICE void warp_walk_ckpt(const DecParams& p, u32* buf, const unsigned short* tab, WalkLane& L, CkptSink& ck)
 {
     const u32 lane = tid() & 31;
-    if (!L.have) { L.qB = 0; L.q = 0xffffffffu; }
+    if (!L.have) { L.qA = 0; L.qB = 0; L.q = 0xffffffffu; }
     const u32 my_rounds = L.have ? ((L.qB + 31) >> 5) / WALK_ROUND_STRIDE + 1 : 0u;
     const u32 first_round = L.have ? (L.q >> 5) / WALK_ROUND_STRIDE : 0xffffffffu;
     u32 r = warp_min_u32(first_round);
@@ -380,7 +383,6 @@ TRPX_DEVICE void warp_walk_ckpt(const DecParams& p, u32* buf, const unsigned sho
     const saddr_t tab_a = saddr(tab);
     const saddr_t lane_a = saddr(buf) + lane * 4;
     const u32 sub = 1u << ck.sh;
-    u32 q_event = L.entered ? 0xffffffffu : L.qA;           // the segment's first bit (afterwards only runs of empty blocks are special)
     u32 q_ck = 0xffffffffu;                                 // position of the next sub-segment boundary; armed on entry
     uint4 pre[8];
     walk_fetch(p, L, r, pre);
@@ -391,45 +393,67 @@ TRPX_DEVICE void warp_walk_ckpt(const DecParams& p, u32* buf, const unsigned sho
         if (r + 1 < r_end) walk_fetch(p, L, r + 1, pre);    // in flight while this round is walked
         const u32 w0 = r * WALK_ROUND_STRIDE;
         const u32 q_round = (w0 + 31) << 5;                 // headers below this bit are readable in this round
-        const u32 qlim = L.qB < q_round ? L.qB : q_round;
         const saddr_t col_a = lane_a - w0 * (WALK_PITCH * 4);
-        for (;;) {
-            if (!any_lane(L.q < qlim)) break;
+        // ---- phase A: warm-up, until the first header at or after the segment's first bit
+        if (any_lane(!L.entered)) {
+            const u32 limA = L.entered ? 0u : (L.qA < q_round ? L.qA : q_round);
+            while (any_lane(L.q < limA)) {
 #pragma unroll
-            for (int rep = 0; rep < 2; ++rep) {             // two steps per vote
-                if (L.q < qlim) {
-                    const saddr_t a = col_a + (L.q >> 5) * (WALK_PITCH * 4);
-                    const u32 win = funnel_r(lds_u32(a), lds_u32_at<WALK_PITCH * 4>(a), L.q);
-                    const bool isrun = L.s == 0 && (win & 1);
-                    if (L.q >= q_event || isrun) {          // ---- rare: entering the segment, runs of empty blocks
-                        if (!L.entered && L.q >= L.qA) { L.entered = true; L.q_entry = L.q; L.s_entry = L.s; L.n = 0; }
-                        if (L.entered) ck.sync_rel();
-                        if (isrun) {                        // a run of '1' headers of empty blocks, 1 bit each
-                            const u32 stop = L.entered ? L.qB : L.qA;
+                for (int rep = 0; rep < 2; ++rep) {
+                    if (L.q < limA) {
+                        const saddr_t a = col_a + (L.q >> 5) * (WALK_PITCH * 4);
+                        const u32 win = funnel_r(lds_u32(a), lds_u32_at<WALK_PITCH * 4>(a), L.q);
+                        if (L.s == 0 && (win & 1)) {        // a run of one-bit headers of empty blocks: never past the segment's first bit
                             u32 run = (u32)ffs32(~win) - 1; // ffs32(0) == 0 -> 0xffffffff: all 32 bits set
                             run = run > 32u ? 32u : run;
-                            run = run > stop - L.q ? stop - L.q : run;
-                            if (L.entered) ck.run(L.q - L.qA, L.n, run);
+                            run = run > L.qA - L.q ? L.qA - L.q : run;
                             L.q += run;
-                            L.n += run;
+                        } else {
+                            const u32 e = lds_u16(tab_a + ((win & (HDR_TAB_ENTRIES - 1)) << 1));
+                            L.s = (e & HDR_SAME) ? L.s : e >> 8;
+                            L.q += (e & 15) + L.s * blk;
                         }
-                        q_event = L.entered ? 0xffffffffu : L.qA;
-                        q_ck = L.entered && ck.next_rel != 0xffffffffu ? L.qA + ck.next_rel : 0xffffffffu;
-                        if (isrun) continue;
                     }
-                    const u32 e = lds_u16(tab_a + ((win & (HDR_TAB_ENTRIES - 1)) << 1));
-                    const u32 s_new = (e & HDR_SAME) ? L.s : e >> 8;
-                    if (L.q >= q_ck) {                      // this header opens sub-segment next_m (and, rarely, more than one)
-                        const u32 rel = L.q - L.qA;
-                        do {
-                            ck.row[ck.next_m] = pack_ckpt(rel, L.s, L.n);
-                            ++ck.next_m;
-                            q_ck = ck.next_m < ck.subs ? q_ck + sub : 0xffffffffu;
-                        } while (L.q >= q_ck);
+                }
+            }
+            if (!L.entered && L.q >= L.qA && L.have) {      // this header is the segment's entry
+                L.entered = true; L.q_entry = L.q; L.s_entry = L.s; L.n = 0;
+                ck.sync_rel();
+                q_ck = ck.next_rel != 0xffffffffu ? L.qA + ck.next_rel : 0xffffffffu;
+            }
+        }
+        // ---- phase B: the segment itself
+        const u32 limB = !L.entered ? 0u : (L.qB < q_round ? L.qB : q_round);
+        while (any_lane(L.q < limB)) {
+#pragma unroll
+            for (int rep = 0; rep < 2; ++rep) {
+                if (L.q < limB) {
+                    const saddr_t a = col_a + (L.q >> 5) * (WALK_PITCH * 4);
+                    const u32 win = funnel_r(lds_u32(a), lds_u32_at<WALK_PITCH * 4>(a), L.q);
+                    if (L.s == 0 && (win & 1)) {            // a run of one-bit headers of empty blocks
+                        u32 run = (u32)ffs32(~win) - 1;
+                        run = run > 32u ? 32u : run;
+                        run = run > L.qB - L.q ? L.qB - L.q : run;
+                        ck.sync_rel();
+                        ck.run(L.q - L.qA, L.n, run);
+                        q_ck = ck.next_rel != 0xffffffffu ? L.qA + ck.next_rel : 0xffffffffu;
+                        L.q += run;
+                        L.n += run;
+                    } else {
+                        const u32 e = lds_u16(tab_a + ((win & (HDR_TAB_ENTRIES - 1)) << 1));
+                        const u32 s_new = (e & HDR_SAME) ? L.s : e >> 8;
+                        if (L.q >= q_ck) {                  // this header opens sub-segment next_m (and, rarely, more than one)
+                            const u32 rel = L.q - L.qA;
+                            do {
+                                ck.row[ck.next_m] = pack_ckpt(rel, L.s, L.n);
+                                ++ck.next_m;
+                                q_ck = ck.next_m < ck.subs ? q_ck + sub : 0xffffffffu;
+                            } while (L.q >= q_ck);
+                        }
+                        L.q += (e & 15) + s_new * blk;
+                        L.n += 1;
+                        L.s = s_new;
                     }
-                    L.q += (e & 15) + s_new * blk;
-                    L.n += 1;
-                    L.s = s_new;
                 }
             }
         }
@@ -519,11 +543,17 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_walk_kernel(DecParams p)
     u64 delta = 0;                                          // frame-relative bit = q + delta
     if (L.have) {
         const SegInfo g = seg_info(p, j);
-        const u64 back = (u64)p.warm_bytes * 8 < g.r0 ? (u64)p.warm_bytes * 8 : g.r0;
+        const u64 warm_bits = (u64)p.warm_bytes * 8;
+        const u64 back = warm_bits < g.r0 ? warm_bits : g.r0;
         const u64 start_bit = g.base_bit + g.r0 - back;     // absolute; a multiple of 8
-        L.cb = (start_bit >> 3) & ~15ull;
-        delta = g.r0 - back - (start_bit - L.cb * 8);
+        // A frame's first segment has no warm-up (its start is exact).  Its lane still counts its rounds from
+        // where a warm-up WOULD have started, so that all lanes of a warp reach their segments in the same round
+        // (the walk loop has a warm-up phase and a segment phase per round; the lane idles through the first).
+        const u64 seg_bit = g.base_bit + g.r0;
+        const u64 origin_bit = seg_bit >= warm_bits ? seg_bit - warm_bits : 0;
+        L.cb = (origin_bit >> 3) & ~15ull;
         L.q = (u32)(start_bit - L.cb * 8);
+        delta = g.r0 - back - (u64)L.q;                     // (mod 2^64: the origin may lie before the frame)
         L.qA = (u32)(g.r0 - delta);
         L.qB = (u32)(g.r1 - delta);
     }
