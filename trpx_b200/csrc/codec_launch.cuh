@@ -20,7 +20,17 @@ enum { DT_U8 = 0, DT_U16, DT_U32, DT_U64, DT_I8, DT_I16, DT_I32, DT_I64 };
 inline size_t dtype_size(int dt) { return dt < 0 || dt > 7 ? 0 : (size_t)1 << (dt & 3); }
 inline bool dtype_signed(int dt) { return dt >= DT_I8; }
 
-constexpr int ENC_NT = 256;     // threads per encoder CTA (8 warps, 48 bytes of pixels per thread)
+#ifndef ENC_NT_U16
+#define ENC_NT_U16 192
+#endif
+#ifndef ENC_NT_U8
+#define ENC_NT_U8 256
+#endif
+#ifndef ENC_NT_U32
+#define ENC_NT_U32 192
+#endif
+constexpr int ENC_NT = 256;     // worker threads per encoder CTA (8 warps; a thread owns 48 or 96 bytes of pixels)
+template <typename T> struct EncNT { static constexpr int V = sizeof(T) == 2 ? ENC_NT_U16 : sizeof(T) == 1 ? ENC_NT_U8 : sizeof(T) == 4 ? ENC_NT_U32 : ENC_NT; };
 constexpr int GEN_NT = 256;     // threads per generic-encoder CTA (one block per thread)
 
 struct Launcher {
@@ -62,9 +72,9 @@ inline EncPlan enc_plan_t(const void* d_pixels, u64 n_values, u64 n_frames, u32 
     pl.nblocks = div_up(n_values, block);
     pl.fast = block == 12 && ((uintptr_t)d_pixels & 15) == 0 && ((n_values * sizeof(T)) & 15) == 0;
     if (pl.fast) {
-        pl.tile_blocks = EncGeom<T, ENC_NT>::TILE_BLOCKS;
-        pl.smem = EncGeom<T, ENC_NT>::SMEM_BYTES;
-        pl.threads = EncGeom<T, ENC_NT>::THREADS;
+        pl.tile_blocks = EncGeom<T, EncNT<T>::V>::TILE_BLOCKS;
+        pl.smem = EncGeom<T, EncNT<T>::V>::SMEM_BYTES;
+        pl.threads = EncGeom<T, EncNT<T>::V>::THREADS;
     } else {
         pl.threads = GEN_NT;
         const u64 maxbits = 12 + (u64)block * (Pix<T>::W + (Pix<T>::SGN ? 1 : 0));
@@ -105,7 +115,7 @@ inline void encode_launch_t(Launcher& L, const EncPlan& pl, EncParams p, u32 cta
     if (grid > pl.n_tiles) grid = pl.n_tiles;
     if (grid == 0) return;
     if (pl.fast)
-        L.err = launch(terse_encode_kernel<T, ENC_NT>, (u32)grid, pl.threads, pl.smem, L.stream, p);
+        L.err = launch(terse_encode_kernel<T, EncNT<T>::V>, (u32)grid, pl.threads, pl.smem, L.stream, p);
     else
         L.err = launch(terse_encode_generic_kernel<T, GEN_NT>, (u32)grid, GEN_NT, pl.smem, L.stream, p,
                        pl.tile_blocks);
@@ -115,7 +125,7 @@ inline void encode_launch_t(Launcher& L, const EncPlan& pl, EncParams p, u32 cta
 template <typename T>
 inline const void* enc_kernel_t(bool fast)
 {
-    return fast ? (const void*)terse_encode_kernel<T, ENC_NT> : (const void*)terse_encode_generic_kernel<T, GEN_NT>;
+    return fast ? (const void*)terse_encode_kernel<T, EncNT<T>::V> : (const void*)terse_encode_generic_kernel<T, GEN_NT>;
 }
 inline const void* enc_kernel(int dtype, bool fast)
 {

@@ -24,6 +24,13 @@
 
 #include "simt.cuh"
 
+#ifndef ENC_UNIT_U8
+#define ENC_UNIT_U8 48
+#endif
+#ifndef ENC_UNIT_U32
+#define ENC_UNIT_U32 96
+#endif
+
 namespace trpx {
 
 // ------------------------------------------------------------------ look-back descriptors
@@ -81,7 +88,7 @@ struct Pix {
     static constexpr int SZ = (int)sizeof(T);
     static constexpr int W = 8 * SZ;
     static constexpr bool SGN = T(-1) < T(0);
-    static constexpr int UNIT_BYTES = (SZ == 8 || SZ == 2) ? 96 : 48;    // bytes one thread owns (3 or 6 LDS.128)
+    static constexpr int UNIT_BYTES = SZ == 8 ? 96 : SZ == 2 ? 96 : SZ == 1 ? ENC_UNIT_U8 : ENC_UNIT_U32;    // bytes one thread owns (3 or 6 LDS.128)
     static constexpr int UW = UNIT_BYTES / 4;               // 32-bit words per unit
     static constexpr int VPU = UNIT_BYTES / SZ;             // values per unit: 48 / 24 / 12 / 12
     static constexpr int BPU = VPU / 12;                    // blocks per unit:  4 /  2 /  1 /  1
@@ -514,7 +521,7 @@ struct EncGeom {
     // for a typical 512^2 u16 tile, WORST_WORDS when nothing compresses.  The ring always holds two
     // worst-case tiles; with typical data ENC_DEPTH tiles are in flight.
     static constexpr int WORST_WORDS = ((TILE_BLOCKS * P::MAXBITS + 31) / 32 + 1 + 3 + 3) / 4 * 4;
-    static constexpr int RING_WORDS = (2 * WORST_WORDS <= 8192 || (P::SZ == 2 && WORST_WORDS <= 8192)) ? 8192 : (2 * WORST_WORDS <= 16384 ? 16384 : 32768);   // a power of two
+    static constexpr int RING_WORDS = (2 * WORST_WORDS <= 8192 || (P::SZ <= 4 && WORST_WORDS <= 8192)) ? 8192 : (2 * WORST_WORDS <= 16384 ? 16384 : 32768);   // a power of two
     static constexpr int SMEM_BYTES = SM_HEADER + ENC_STAGES * STAGE_BYTES + RING_WORDS * 4;
     static constexpr int THREADS = NT + 32 * ENC_RESOLVERS;   // worker warps + resolver warps
 };
@@ -532,7 +539,7 @@ struct EncGeom {
 //                          find the tile's stream position with the two-level look-back and exchange the
 //                          boundary word with the neighbour tile: pure latency, off the workers' path.
 template <typename T, int NT>
-TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_RESOLVERS, (sizeof(T) == 2 ? 2 : 3)) terse_encode_kernel(EncParams p)
+TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_RESOLVERS, (EncGeom<T, NT>::SMEM_BYTES > 75 * 1024 ? 2 : 3)) terse_encode_kernel(EncParams p)
 {
     typedef Pix<T> P;
     typedef EncGeom<T, NT> G;
