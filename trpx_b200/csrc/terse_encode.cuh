@@ -144,25 +144,27 @@ TRPX_HD void block_header(u32 s, u32 prev, u32& hv, u32& hl)
 // its predecessor) which stays in `head`, and the unfinished LAST word which stays in `acc`; both
 // are resolved by merge_and_flush().
 struct BitSink {
-    u32* stg;
+    u32* stg;               // (merge_and_flush reaches the head / tail words through it)
+    saddr_t wp;             // shared-window address of the unfinished word
     u32 lo;                 // the unfinished word: nb < 32 valid bits
-    u32 w, nb, w0, head;
+    u32 nb, w0, head;
     bool crossed;
     TRPX_DEVICE void init(u32* stg_, u32 off)
     {
-        stg = stg_; w0 = w = off >> 5; nb = off & 31; lo = 0; head = 0; crossed = false;
+        stg = stg_; w0 = off >> 5; wp = saddr(stg_) + w0 * 4; nb = off & 31; lo = 0; head = 0; crossed = false;
     }
     TRPX_DEVICE void put(u32 v, u32 n)     // n in [0, 32], v < 2^n
     {
         const u32 a0 = lo | (v << nb);
         const u32 a1 = funnel_l(v, 0u, nb);                     // v >> (32 - nb); 0 when nb == 0
-        nb += n;
-        const bool p1 = nb >= 32;
-        if (p1) { if (crossed) stg[w] = a0; else head = a0; }
-        crossed = crossed || p1;
-        lo = p1 ? a1 : a0;
-        w += p1 ? 1u : 0u;
-        nb &= 31;
+        const u32 t = nb + n;                                   // < 64
+        const bool c1 = t >= 32;
+        if (c1 && crossed) sts_u32_weak(wp, a0);
+        if (c1 && !crossed) head = a0;
+        crossed = crossed || c1;
+        lo = c1 ? a1 : a0;
+        wp += (t >> 3) & 4u;                                    // one word further when a word completed
+        nb = t & 31;
     }
     // n in [0, 64], v < 2^n.  Same contract as put(); up to two words complete per call.  Straight-line
     // code (selects and predicated stores), so lanes with different widths stay converged.
@@ -172,14 +174,15 @@ struct BitSink {
         const u32 a0 = lo | (v0 << nb);                         // bits  0..31 of lo | v << nb
         const u32 a1 = funnel_l(v0, v1, nb);                    // bits 32..63
         const u32 a2 = funnel_l(v1, 0u, nb);                    // bits 64..95
-        nb += n;
-        const u32 c = nb >> 5;                                  // complete words: 0, 1 or 2
-        if (c >= 1) { if (crossed) stg[w] = a0; else head = a0; }
-        if (c >= 2) stg[w + 1] = a1;
-        crossed = crossed || c >= 1;
-        lo = c == 0 ? a0 : (c == 1 ? a1 : a2);
-        w += c;
-        nb &= 31;
+        const u32 t = nb + n;                                   // < 96
+        const bool c1 = t >= 32, c2 = t >= 64;
+        if (c1 && crossed) sts_u32_weak(wp, a0);
+        if (c1 && !crossed) head = a0;
+        if (c2) sts_u32_weak(wp + 4, a1);
+        crossed = crossed || c1;
+        lo = c2 ? a2 : (c1 ? a1 : a0);
+        wp += (t >> 3) & 12u;                                   // 4 bytes per completed word (0, 1 or 2)
+        nb = t & 31;
     }
     TRPX_DEVICE void put_wide(u64 v, u32 s)   // low s bits of the sign-extended value, s in [1, 65]
     {
