@@ -133,6 +133,11 @@ TRPX_DEVICE u32 lds_u16(saddr_t a)
 TRPX_DEVICE void sts_u32(saddr_t a, u32 x) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(x) : "memory"); }
 // (no memory clobber: for write-only staging that is read back only after a barrier)
 TRPX_DEVICE void sts_u32_weak(saddr_t a, u32 x) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(x)); }
+// the same, predicated inside the asm: straight-line code, no branch around the store
+TRPX_DEVICE void sts_u32_if(bool c, saddr_t a, u32 x)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u32 [%0], %1;\n\t}" ::"r"(a), "r"(x), "r"((u32)c));
+}
 TRPX_DEVICE void sts_v2(saddr_t a, u32 x, u32 y)
 {
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
@@ -348,6 +353,7 @@ template <int OFF> inline u32 lds_u32_at(saddr_t a) { return *(const u32*)saddr_
 inline u32 lds_u16(saddr_t a) { return *(const unsigned short*)saddr_ptr(a, 2); }
 inline void sts_u32(saddr_t a, u32 x) { *(u32*)saddr_ptr(a, 4) = x; }
 inline void sts_u32_weak(saddr_t a, u32 x) { *(u32*)saddr_ptr(a, 4) = x; }
+inline void sts_u32_if(bool c, saddr_t a, u32 x) { if (c) *(u32*)saddr_ptr(a, 4) = x; }
 inline void sts_v2(saddr_t a, u32 x, u32 y) { u32* d = (u32*)saddr_ptr(a, 8); d[0] = x; d[1] = y; }
 inline void sts_v4(saddr_t a, u32 x, u32 y, u32 z, u32 w) { u32* d = (u32*)saddr_ptr(a, 16); d[0] = x; d[1] = y; d[2] = z; d[3] = w; }
 inline u32 low_mask(u32 n) { return n >= 32 ? 0xffffffffu : (1u << n) - 1; }

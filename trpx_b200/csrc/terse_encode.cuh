@@ -159,8 +159,8 @@ struct BitSink {
         const u32 a1 = funnel_l(v, 0u, nb);                     // v >> (32 - nb); 0 when nb == 0
         const u32 t = nb + n;                                   // < 64
         const bool c1 = t >= 32;
-        if (c1 && crossed) sts_u32_weak(wp, a0);
-        if (c1 && !crossed) head = a0;
+        sts_u32_if(c1 && crossed, wp, a0);
+        head = c1 && !crossed ? a0 : head;
         crossed = crossed || c1;
         lo = c1 ? a1 : a0;
         wp += (t >> 3) & 4u;                                    // one word further when a word completed
@@ -176,9 +176,9 @@ struct BitSink {
         const u32 a2 = funnel_l(v1, 0u, nb);                    // bits 64..95
         const u32 t = nb + n;                                   // < 96
         const bool c1 = t >= 32, c2 = t >= 64;
-        if (c1 && crossed) sts_u32_weak(wp, a0);
-        if (c1 && !crossed) head = a0;
-        if (c2) sts_u32_weak(wp + 4, a1);
+        sts_u32_if(c1 && crossed, wp, a0);
+        head = c1 && !crossed ? a0 : head;
+        sts_u32_if(c2, wp + 4, a1);
         crossed = crossed || c1;
         lo = c2 ? a2 : (c1 ? a1 : a0);
         wp += (t >> 3) & 12u;                                   // 4 bytes per completed word (0, 1 or 2)
