@@ -137,6 +137,32 @@ TRPX_HD void block_header(u32 s, u32 prev, u32& hv, u32& hl)
     else if (s < 10) { hv = (0x7u | ((s - 7) << 3)) << 1; hl = 6; }
     else { hv = (0x1Fu | ((s - 10) << 5)) << 1; hl = 12; }
 }
+// The explicit headers of all widths (0 .. 73) as a constant table, value | length << 16: the hot loop replaces
+// the compare / select chain above by one indexed constant load and one select for "same width as before".
+struct EncHdrTab { u32 v[80]; };
+constexpr EncHdrTab make_enc_hdr_tab()
+{
+    EncHdrTab t{};
+    for (u32 s = 0; s < 80; ++s) {
+        u32 hv = 0, hl = 0;
+        if (s < 7) { hv = s << 1; hl = 4; }
+        else if (s < 10) { hv = (0x7u | ((s - 7) << 3)) << 1; hl = 6; }
+        else { hv = (0x1Fu | ((s - 10) << 5)) << 1; hl = 12; }
+        t.v[s] = hv | (hl << 16);
+    }
+    return t;
+}
+#ifndef TRPX_EMU
+__constant__ EncHdrTab enc_hdr_tab = make_enc_hdr_tab();
+#else
+static const EncHdrTab enc_hdr_tab = make_enc_hdr_tab();
+#endif
+TRPX_DEVICE void block_header_fast(u32 s, u32 prev, u32& hv, u32& hl)      // s <= 73
+{
+    const u32 e = s == prev ? 0x00010001u : enc_hdr_tab.v[s];
+    hv = e & 0xffffu;
+    hl = e >> 16;
+}
 
 // ------------------------------------------------------------------ K4: per-thread bit sink
 // Appends fields LSB-first (Bit_pointer.hpp:700-730) at a tile-relative bit offset.  Complete
@@ -708,7 +734,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_RESOLVERS, (EncGeom<T, NT>::SM
         for (int b = 0; b < P::BPU; ++b) {
             hv[b] = 0; hl[b] = 0;
             if (cnt[b]) {
-                block_header(sb[b], prev, hv[b], hl[b]);
+                block_header_fast(sb[b], prev, hv[b], hl[b]);
                 len += hl[b] + sb[b] * cnt[b];
                 prev = sb[b];
             }
