@@ -1132,11 +1132,11 @@ struct SliceDesc {
 };
 constexpr u32 UNP_CHUNKS = (UNP_SPAN_WORDS / 4 + UNP_NT - 1) / UNP_NT;    // 16-byte pieces of the slice per thread
 
-TRPX_DEVICE SliceDesc load_slice_desc(const DecParams& p, u32 sl, u32 parts)
+TRPX_DEVICE SliceDesc load_slice_desc(const DecParams& p, u32 seg, u32 h)     // slice h of segment seg
 {
     SliceDesc d;
-    const u64 j = sl / parts;
-    d.h = sl % parts;
+    const u64 j = seg;
+    d.h = h;
     const u64* sd = p.segd + j * 4;                                  // count 0 past the last segment
     d.seg_bit = sd[0]; d.frame_end_bit = sd[1]; d.b0 = sd[2];
     const u64 fc = sd[3];
@@ -1216,8 +1216,14 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 3) prolix_unpack_seg_kernel(DecParam
     if (sl >= total) return;
     copy_header_table<UNP_NT>(tab, p.hdr_tab);
 
-    SliceDesc d0 = load_slice_desc(p, sl, parts), d1 = d0, d2 = d0;
-    if (sl + step < total && sl + step >= sl) d1 = load_slice_desc(p, sl + step, parts);
+    // slices sl, sl + step, ... : (segment, slice-in-segment) pairs advanced incrementally, iterations counted down
+    const u32 step_j = step / parts, step_h = step % parts;
+    u32 left = (total - 1 - sl) / step;                             // iterations after this one
+    u32 nj = sl / parts, nh = sl % parts;                           // the slice the next load_slice_desc() is for
+    auto advance = [&]() { nj += step_j; nh += step_h; if (nh >= parts) { nh -= parts; ++nj; } };
+    SliceDesc d0 = load_slice_desc(p, nj, nh), d1 = d0, d2 = d0;
+    advance();
+    if (left >= 1) { d1 = load_slice_desc(p, nj, nh); advance(); }
     uint4 pre[UNP_CHUNKS];
     const u32 sub_shift = p.sub_shift;
     const bool sparse = sub_shift < SUB_SHIFT_MAX;
@@ -1225,9 +1231,8 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 3) prolix_unpack_seg_kernel(DecParam
     const u32 pos_limit = (((u32)UNP_NT << (sub_shift - 3)) + 16) * 8;                    // no header is read past this bit
     fetch_slice(p, slice_a0(d0, sub_shift), span_chunks, pre);
     for (;;) {
-        const bool have1 = sl + step < total && sl + step >= sl;
-        const bool have2 = have1 && sl + 2 * step < total && sl + 2 * step >= sl + step;
-        if (have2) d2 = load_slice_desc(p, sl + 2 * step, parts);   // arrives during this iteration
+        const bool have1 = left >= 1, have2 = left >= 2;
+        if (have2) { d2 = load_slice_desc(p, nj, nh); advance(); }   // arrives during this iteration
         const u64 a0 = slice_a0(d0, sub_shift);
         stage_slice(span, span_chunks, pre);          // (nobody reads the span any more: every thread is past the barrier that followed the unpack loop)
         if (t == 0) bulk_wait_read0();                // the previous slice's bulk store has finished reading the output stage
@@ -1340,7 +1345,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 3) prolix_unpack_seg_kernel(DecParam
             }
         }
         if (!have1) break;
-        sl += step;
+        --left;
         d0 = d1;
         d1 = d2;
     }
