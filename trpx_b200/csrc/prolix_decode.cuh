@@ -1060,25 +1060,22 @@ TRPX_DEVICE void unpack_block12(const u32* sp, saddr_t col_a, u32 rel, u32 pos, 
 {
     constexpr u32 SO = sizeof(O);
     const bool in_rows = rel + 12 * s + 32 <= UNP_ROWS * 32;      // the whole block is inside the column's 20 rows
-    if (SO == 2 && s <= 16 && in_rows) {
-        // two fields of s bits -> two 16-bit lanes with one multiply-add (the encoder's trick reversed)
+    if (SO == 2 && s <= 16 && rel + 8 * s + 96 <= UNP_ROWS * 32) {
+        // Four fields (4s <= 64 bits) per 64-bit window, three windows per block -- the same code for every width, so
+        // lanes with narrow and wide blocks stay converged.  Two fields of s bits become two 16-bit lanes with one
+        // multiply-add (the encoder's trick reversed).
         const u32 m2 = low_mask(2 * s);
         const u32 K = 65536u - (1u << s);
         u32 o[6];
-        if (s <= 8) {                                     // a 32-bit window holds four fields: three windows per block
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const u32 q = col_window(col_a, rel + 4 * s * i);
-                const u32 p0 = q & m2, p1 = (q >> (2 * s)) & m2;
-                o[2 * i] = p0 + (p0 >> s) * K;
-                o[2 * i + 1] = p1 + (p1 >> s) * K;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 6; ++i) {
-                const u32 pm = col_window(col_a, rel + 2 * s * i) & m2;
-                o[i] = pm + (pm >> s) * K;
-            }
+        for (int i = 0; i < 3; ++i) {
+            const u32 r = rel + 4 * s * i;
+            const saddr_t a = col_a + (r >> 5) * (UNP_CP * 4);
+            const u32 w0 = lds_u32(a), w1 = lds_u32_at<UNP_CP * 4>(a), w2 = lds_u32_at<UNP_CP * 8>(a);
+            const u32 lo = funnel_r(w0, w1, r), hi = funnel_r(w1, w2, r);
+            const u32 p0 = lo & m2, p1 = funnel_rc(lo, hi, 2 * s) & m2;
+            o[2 * i] = p0 + (p0 >> s) * K;
+            o[2 * i + 1] = p1 + (p1 >> s) * K;
         }
         if (SGN) {
             const u32 KS = (0xffffu << s) & 0xffffu;      // sign extension of a 16-bit lane

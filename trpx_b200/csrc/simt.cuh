@@ -71,6 +71,7 @@ TRPX_DEVICE int ffs64(u64 x) { return __ffsll((long long)x); }
 TRPX_DEVICE int popc32(u32 x) { return __popc(x); }
 TRPX_DEVICE u32 funnel_r(u32 lo, u32 hi, u32 sh) { return __funnelshift_r(lo, hi, sh); }   // sh & 31
 TRPX_DEVICE u32 funnel_l(u32 lo, u32 hi, u32 sh) { return __funnelshift_l(lo, hi, sh); }   // (hi:lo << sh) >> 32
+TRPX_DEVICE u32 funnel_rc(u32 lo, u32 hi, u32 sh) { return __funnelshift_rc(lo, hi, sh); } // (hi:lo >> min(sh, 32)), low word
 TRPX_DEVICE u32 vabs2(u32 x) { return __vabs2(x); }   // |.| per signed 16-bit half (wraps for -32768)
 TRPX_DEVICE u32 vabs4(u32 x) { return __vabs4(x); }   // |.| per signed byte
 
@@ -305,6 +306,7 @@ inline u32 funnel_r(u32 lo, u32 hi, u32 sh)
     sh &= 31;
     return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
 }
+inline u32 funnel_rc(u32 lo, u32 hi, u32 sh) { return sh >= 32 ? hi : (sh ? (lo >> sh) | (hi << (32 - sh)) : lo); }
 inline u32 funnel_l(u32 lo, u32 hi, u32 sh)
 {
     sh &= 31;
