@@ -1135,15 +1135,16 @@ TRPX_DEVICE SliceDesc load_slice_desc(const DecParams& p, u32 seg, u32 h)     //
     const u64 j = seg;
     d.h = h;
     const u64* sd = p.segd + j * 4;                                  // count 0 past the last segment
-    d.seg_bit = sd[0]; d.frame_end_bit = sd[1]; d.b0 = sd[2];
-    const u64 fc = sd[3];
+    // (opaque loads: these values are consumed two iterations later and must stay in flight until then)
+    d.seg_bit = ldg_u64_opaque(sd); d.frame_end_bit = ldg_u64_opaque(sd + 1); d.b0 = ldg_u64_opaque(sd + 2);
+    const u64 fc = ldg_u64_opaque(sd + 3);
     d.frame = (u32)fc; d.seg_cnt = (u32)(fc >> 32);
     const u64* row = p.ckpt + j * p.subs_per_seg;
     const u32 m = d.h * UNP_NT + tid();
-    d.rowA = d.h * UNP_NT < p.subs_per_seg ? row[d.h * UNP_NT] : ~0ull;
-    d.rowB = (d.h + 1) * UNP_NT < p.subs_per_seg ? row[(d.h + 1) * UNP_NT] : ~0ull;
-    d.c0 = m < p.subs_per_seg ? row[m] : ~0ull;
-    d.c1 = m + 1 < p.subs_per_seg ? row[m + 1] : ~0ull;
+    d.rowA = d.h * UNP_NT < p.subs_per_seg ? ldg_u64_opaque(row + d.h * UNP_NT) : ~0ull;
+    d.rowB = (d.h + 1) * UNP_NT < p.subs_per_seg ? ldg_u64_opaque(row + (d.h + 1) * UNP_NT) : ~0ull;
+    d.c0 = m < p.subs_per_seg ? ldg_u64_opaque(row + m) : ~0ull;
+    d.c1 = m + 1 < p.subs_per_seg ? ldg_u64_opaque(row + m + 1) : ~0ull;
     return d;
 }
 TRPX_DEVICE u64 slice_a0(const SliceDesc& d, u32 sub_shift)      // 16-byte aligned byte offset of the slice's first word in the payload

@@ -98,6 +98,14 @@ TRPX_DEVICE u32 ld_relaxed(const u32* p)
     return v;
 }
 
+// A global load the compiler cannot reason about (it would otherwise turn loads from CTA-uniform addresses into
+// uniform-register values at once -- and wait for them -- which defeats a software prefetch).
+TRPX_DEVICE u64 ldg_u64_opaque(const u64* p)
+{
+    u64 v;
+    asm volatile("ld.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
 // streaming (read-once / write-once) global accesses: keep them out of L1
 TRPX_DEVICE u32 ld_stream(const u32* p) { return __ldcs(p); }
 TRPX_DEVICE void st_stream(u32* p, u32 v) { __stcs(p, v); }
@@ -359,6 +367,7 @@ inline void sts_u32_if(bool c, saddr_t a, u32 x) { if (c) *(u32*)saddr_ptr(a, 4)
 inline void sts_v2(saddr_t a, u32 x, u32 y) { u32* d = (u32*)saddr_ptr(a, 8); d[0] = x; d[1] = y; }
 inline void sts_v4(saddr_t a, u32 x, u32 y, u32 z, u32 w) { u32* d = (u32*)saddr_ptr(a, 16); d[0] = x; d[1] = y; d[2] = z; d[3] = w; }
 inline u32 low_mask(u32 n) { return n >= 32 ? 0xffffffffu : (1u << n) - 1; }
+inline u64 ldg_u64_opaque(const u64* p) { return *p; }
 inline u32 ld_stream(const u32* p) { return *p; }
 inline void st_stream(u32* p, u32 v) { *p = v; }
 inline void st_stream(uint4* p, uint4 v) { *p = v; }
