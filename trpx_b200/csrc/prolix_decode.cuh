@@ -467,45 +467,42 @@ template <int NT>
 TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_segments_kernel(DecParams p)
 {
     TRPX_SHARED u64 sm_tot[NT / 32];
-    TRPX_SHARED u64 sm_run;
     const u32 t = tid(), lane = t & 31, warp = t >> 5;
-    if (t == 0) sm_run = 0;
     build_header_table<NT>(p.hdr_tab);                       // the walkers copy it into shared memory
-    sync_block();
-    for (u64 f0 = 0; f0 < p.n_frames; f0 += NT) {
-        const u64 f = f0 + t;
-        u64 nseg = 0;
-        if (f < p.n_frames) {
-            const u64 e = p.frame_ends[f], b = f ? p.frame_ends[f - 1] : 0;
-            if (e <= b || e > p.payload_bytes) atomic_max(p.status, DEC_MALFORMED);
-            else nseg = div_up(e - b, p.seg_bytes);
-        }
-        u64 incl = nseg;
+    // thread t owns the frames [f0, f1): their segment counts, one block-wide scan of the per-thread sums, then
+    // the table entries -- one round whatever the number of frames
+    const u64 per = div_up(p.n_frames, (u64)NT);
+    const u64 f0 = (u64)t * per < p.n_frames ? (u64)t * per : p.n_frames;
+    const u64 f1 = f0 + per < p.n_frames ? f0 + per : p.n_frames;
+    auto nseg_of = [&](u64 f) -> u64 {
+        const u64 e = p.frame_ends[f], b = f ? p.frame_ends[f - 1] : 0;
+        if (e <= b || e > p.payload_bytes) { atomic_max(p.status, DEC_MALFORMED); return 0; }
+        return div_up(e - b, p.seg_bytes);
+    };
+    u64 mine = 0;
+    for (u64 f = f0; f < f1; ++f) mine += nseg_of(f);
+    u64 incl = mine;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            u64 v = shfl_up(incl, d);
-            if (lane >= (u32)d) incl += v;
-        }
-        if (lane == 31) sm_tot[warp] = incl;
-        sync_block();
-        u64 base = sm_run, total = 0;
-        for (int i = 0; i < NT / 32; ++i) {
-            u64 v = sm_tot[i];
-            if ((u32)i < warp) base += v;
-            total += v;
-        }
-        const u64 first = base + incl - nseg;
-        if (f < p.n_frames) {
-            p.seg_base[f] = first;
-            for (u64 i = 0; i < nseg && first + i < p.max_segs; ++i) p.seg_frame[first + i] = (u32)f;
-        }
-        sync_block();
-        if (t == 0) {
-            sm_run += total;
-            if (f0 + NT >= p.n_frames) p.seg_base[p.n_frames] = sm_run > p.max_segs ? p.max_segs : sm_run;
-        }
-        sync_block();
+    for (int d = 1; d < 32; d <<= 1) {
+        u64 v = shfl_up(incl, d);
+        if (lane >= (u32)d) incl += v;
     }
+    if (lane == 31) sm_tot[warp] = incl;
+    sync_block();
+    u64 base = 0, total = 0;
+    for (int i = 0; i < NT / 32; ++i) {
+        const u64 v = sm_tot[i];
+        if ((u32)i < warp) base += v;
+        total += v;
+    }
+    u64 run = base + incl - mine;
+    for (u64 f = f0; f < f1; ++f) {
+        const u64 nseg = nseg_of(f);
+        p.seg_base[f] = run;
+        for (u64 i = 0; i < nseg && run + i < p.max_segs; ++i) p.seg_frame[run + i] = (u32)f;
+        run += nseg;
+    }
+    if (t == 0) p.seg_base[p.n_frames] = total > p.max_segs ? p.max_segs : total;
 }
 
 struct SegInfo { u64 frame, idx, base_bit, frame_bits, r0, r1; };
