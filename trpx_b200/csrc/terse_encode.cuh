@@ -484,8 +484,9 @@ TRPX_DEVICE void store_tile(const EncParams& p, u64 tile, const TileGeom& g, con
     const u32 k = (u32)(Wn - W0);
     const bool fits = ((Pn + 7) >> 3) <= p.out_capacity;
     if (fits) {
-        for (u32 i = rank; i < k; i += nthr)
-            st_stream(&p.out_words[W0 + i], window_word(stg, nstg, i, sh) | (i == 0 ? tail_in : 0u));
+        u32* outw = p.out_words + W0;
+        if (rank == 0 && k) st_stream(outw, window_word(stg, nstg, 0, sh) | tail_in);   // the word shared with the previous tile
+        for (u32 i = rank ? rank : nthr; i < k; i += nthr) st_stream(outw + i, window_word(stg, nstg, i, sh));
     } else if (rank == 0) {
         atomic_max(p.status, 2u);                          // TRPX_ERR_CAPACITY
     }
