@@ -291,3 +291,60 @@ def test_big_frames_roundtrip_and_oracle(codec, shape, dt, lam):
     assert np.array_equal(d, st)
     d1, _ = codec.decode(p[: int(fb[0])], n, 1, False, dt)
     assert np.array_equal(d1[0], st[0])
+
+
+# ---------------------------------------------------------------- host pipelines: many batches, lane reuse, two contexts
+def test_host_flavour_many_batches_and_lane_reuse(monkeypatch):
+    """One frame per batch (TRPX_BATCH_MB=0) and few lanes: every lane is reused many times, payload copies of
+    uneven sizes land back to back in `out`, every batch has its own status word and frame-end slice."""
+    monkeypatch.setenv("TRPX_BATCH_MB", "0")
+    monkeypatch.setenv("TRPX_ENC_LANES", "2")
+    monkeypatch.setenv("TRPX_DEC_LANES", "3")
+    c = trpx_b200.Codec(0)
+    try:
+        rng = np.random.default_rng(5)
+        st = np.stack([orc.kat_fill(orc.U16, 12 * 1000 + 8, 300 + f) >> int(rng.integers(0, 12)) for f in range(37)])
+        st[11] = 0
+        roundtrip(c, st)
+        p, fb, pb = c.encode(st)
+        d, _ = c.decode(p, st.shape[1], st.shape[0], False, np.uint16, frame_bytes=fb, first_frame=5, n_frames=29)
+        assert np.array_equal(d, st[5:34])
+        bad = p.copy()
+        bad[int(fb[:20].sum()) + 3:int(fb[:21].sum())] = 0xFF          # frame 20 (its own batch) no longer adds up
+        with pytest.raises(trpx_b200.TrpxError) as e:
+            c.decode(bad, st.shape[1], st.shape[0], False, np.uint16, frame_bytes=fb)
+        assert e.value.status == trpx_b200.ERR_MALFORMED
+        sst = np.stack([orc.synth_frame(orc.I16, 64, 96, 3.0, 0, 9 + f) for f in range(9)])
+        roundtrip(c, sst)
+    finally:
+        c.close()
+
+
+def test_two_contexts_stream_chunks_concurrently(codec):
+    """bench.py's streamed e2e in miniature: one host thread encodes chunk k+1 on its context while a second thread
+    decodes chunk k on another context; the concatenated payload equals the oracle's."""
+    import queue
+    import threading
+    st = np.stack([orc.synth_frame(orc.U16, 256, 256, 2.0, 50, 700 + f) for f in range(24)])
+    other = trpx_b200.Codec(0)
+    q, parts, back = queue.Queue(), [], {}
+
+    def enc_side():
+        for k in range(0, 24, 4):
+            p, fb, pb = codec.encode(st[k:k + 4])
+            parts.append(p)
+            q.put((k, p, fb))
+        q.put(None)
+
+    def dec_side():
+        while (it := q.get()) is not None:
+            k, p, fb = it
+            back[k] = other.decode(p, st.shape[1], 4, False, np.uint16, frame_bytes=fb)[0]
+
+    th = [threading.Thread(target=enc_side), threading.Thread(target=dec_side)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    other.close()
+    want, _, _ = orc.encode_stack(st)
+    assert np.array_equal(np.concatenate(parts), want)
+    assert np.array_equal(np.concatenate([back[k] for k in range(0, 24, 4)]), st)

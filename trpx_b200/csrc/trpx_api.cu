@@ -19,7 +19,8 @@ using namespace trpx;
 
 namespace {
 
-constexpr int N_LANES = 3;
+constexpr int N_LANES = 8;     // lanes of a context (stream + scratch + staging each)
+constexpr int DEV_LANES = 3;   // lanes the *_device entry points may name (trpx_ctx_lanes)
 
 struct DevBuf {
     void* p = nullptr;
@@ -28,6 +29,9 @@ struct DevBuf {
 
 struct Lane {
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // host flavours: payload D2H of the encoder, off the lane's main stream
+    cudaEvent_t ev_drained = nullptr;     // ... recorded there once d_out has been copied out
+    bool drain_pending = false;
     DevBuf enc_scratch, dec_scratch;   // look-back descriptors / P1 tables
     DevBuf d_in, d_out, d_ends;        // staging of the host-pointer flavours
     u32* d_small = nullptr;            // [0] prolix_bits, [1] status
@@ -52,7 +56,13 @@ struct trpx_ctx {
     std::mutex mu;
     u32 sub_shift = 0;                   // 0: chosen per call (TRPX_SUB_SHIFT overrides: 5..8)
     u32 seg_bytes = 0, warm_bytes = 0;   // 0: chosen per call from the stream's mean block size (TRPX_SEG_BYTES / TRPX_WARM_BYTES override)
-    size_t batch_bytes = 256u << 20;   // raw pixel bytes per pipeline batch of the host flavours
+    size_t batch_bytes = 128u << 20;   // raw pixel bytes per pipeline batch of the host flavours (TRPX_BATCH_MB)
+    size_t enc_batch_bytes = 0;        // ... of trpx_encode_host alone (TRPX_ENC_BATCH_MB; 0: batch_bytes)
+    int enc_lanes = 4, dec_lanes = 6;  // batches in flight in the host flavours (TRPX_ENC_LANES / TRPX_DEC_LANES)
+    u64* h_call_ends = nullptr;        // pinned: frame ends of every batch of one trpx_decode_host call
+    size_t h_call_ends_cap = 0;
+    DevBuf d_call_status;              // one status word per batch of a trpx_decode_host call
+    std::vector<u32> call_status;
     u32 coop_grid = 0;
     bool profiling = false;
 };
@@ -168,6 +178,14 @@ Launcher make_launcher(trpx_ctx* c, cudaStream_t s, Lane* lane = nullptr)
     return L;
 }
 
+// Host flavour of the encoder: (frame ends, prolix_bits, status) of a batch go to pinned host memory with plain
+// stores over PCIe instead of a D2H copy, so that the host learns a batch's size without touching a copy engine.
+__global__ void publish_results_kernel(const u64* d_ends, u64 n, const u32* d_small, u64* h_ends, u32* h_small)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) h_ends[i] = d_ends[i];
+    if (blockIdx.x == 0 && threadIdx.x < 2) h_small[threadIdx.x] = d_small[threadIdx.x];
+}
+
 int status_of_device_word(u32 w) { return w == 0 ? TRPX_OK : (int)w; }
 
 }  // namespace
@@ -220,6 +238,8 @@ int trpx_ctx_create(int device, trpx_ctx** out)
     for (int i = 0; i < N_LANES; ++i) {
         Lane& l = c->lanes[i];
         if (!cuda_ok(c, cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking), "cudaStreamCreate") ||
+            !cuda_ok(c, cudaStreamCreateWithFlags(&l.copy_stream, cudaStreamNonBlocking), "cudaStreamCreate") ||
+            !cuda_ok(c, cudaEventCreateWithFlags(&l.ev_drained, cudaEventDisableTiming), "cudaEventCreate") ||
             !cuda_ok(c, cudaMalloc((void**)&l.d_small, 64), "cudaMalloc") ||
             !cuda_ok(c, cudaMallocHost((void**)&l.h_small, 64), "cudaMallocHost")) {
             trpx_ctx_destroy(c);
@@ -230,6 +250,13 @@ int trpx_ctx_create(int device, trpx_ctx** out)
     c->warm_bytes = env_u32("TRPX_WARM_BYTES", 0);
     c->sub_shift = env_u32("TRPX_SUB_SHIFT", 0);
     c->batch_bytes = (size_t)env_u32("TRPX_BATCH_MB", (u32)(c->batch_bytes >> 20)) << 20;
+    c->enc_batch_bytes = getenv("TRPX_ENC_BATCH_MB") ? (size_t)env_u32("TRPX_ENC_BATCH_MB", 0) << 20 : c->batch_bytes;
+    c->enc_lanes = (int)env_u32("TRPX_ENC_LANES", (u32)c->enc_lanes);
+    c->dec_lanes = (int)env_u32("TRPX_DEC_LANES", (u32)c->dec_lanes);
+    if (c->enc_lanes < 1) c->enc_lanes = 1;
+    if (c->enc_lanes > N_LANES) c->enc_lanes = N_LANES;
+    if (c->dec_lanes < 1) c->dec_lanes = 1;
+    if (c->dec_lanes > N_LANES) c->dec_lanes = N_LANES;
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)prolix_resolve_kernel<RESOLVE_NT>, RESOLVE_NT, 0) != cudaSuccess || occ < 1) {
         cudaGetLastError();
@@ -248,6 +275,8 @@ void trpx_ctx_destroy(trpx_ctx* c)
     for (int i = 0; i < N_LANES; ++i) {
         Lane& l = c->lanes[i];
         if (l.stream) { cudaStreamSynchronize(l.stream); cudaStreamDestroy(l.stream); }
+        if (l.copy_stream) { cudaStreamSynchronize(l.copy_stream); cudaStreamDestroy(l.copy_stream); }
+        if (l.ev_drained) cudaEventDestroy(l.ev_drained);
         DevBuf* bufs[] = {&l.enc_scratch, &l.dec_scratch, &l.d_in, &l.d_out, &l.d_ends};
         for (DevBuf* b : bufs)
             if (b->p) cudaFree(b->p);
@@ -256,12 +285,14 @@ void trpx_ctx_destroy(trpx_ctx* c)
         if (l.h_ends) cudaFreeHost(l.h_ends);
         for (cudaEvent_t e : l.ev_pool) cudaEventDestroy(e);
     }
+    if (c->h_call_ends) cudaFreeHost(c->h_call_ends);
+    if (c->d_call_status.p) cudaFree(c->d_call_status.p);
     delete c;
 }
 
 int trpx_ctx_device(const trpx_ctx* c) { return c ? c->device : -1; }
 const char* trpx_last_error(const trpx_ctx* c) { return c ? c->last_error.c_str() : ""; }
-int trpx_ctx_lanes(const trpx_ctx* c) { return c ? N_LANES : 0; }
+int trpx_ctx_lanes(const trpx_ctx* c) { return c ? DEV_LANES : 0; }
 uint64_t trpx_ctx_launch_count(const trpx_ctx* c) { return c ? c->launches : 0; }
 size_t trpx_ctx_scratch_bytes(const trpx_ctx* c)
 {
@@ -283,7 +314,7 @@ int trpx_ctx_set_profiling(trpx_ctx* c, int on)
 
 int trpx_ctx_last_kernel_times(trpx_ctx* c, int lane, const char** names, float* ms, int cap)
 {
-    if (!c || lane < 0 || lane >= N_LANES) return 0;
+    if (!c || lane < 0 || lane >= DEV_LANES) return 0;
     Lane& l = c->lanes[lane];
     int n = 0;
     for (size_t i = 1; i < l.ev_used && n < cap; ++i) {
@@ -302,7 +333,7 @@ int trpx_encode_device(trpx_ctx* c, int lane, const void* d_pixels, int dtype, s
                        uint64_t* d_frame_ends, uint32_t* d_prolix_bits, uint32_t* d_status, void* stream)
 {
     if (!c) return TRPX_ERR_BAD_ARG;
-    if (lane < 0 || lane >= N_LANES || !d_pixels || !d_out || !d_frame_ends || !d_prolix_bits || !d_status ||
+    if (lane < 0 || lane >= DEV_LANES || !d_pixels || !d_out || !d_frame_ends || !d_prolix_bits || !d_status ||
         !dtype_size(dtype) || !block || !n_values || !n_frames)
         return TRPX_ERR_BAD_ARG;
     if (((uintptr_t)d_out & 15) || ((uintptr_t)d_pixels & (dtype_size(dtype) - 1))) return TRPX_ERR_BAD_ARG;
@@ -324,7 +355,7 @@ int trpx_decode_device(trpx_ctx* c, int lane, const uint8_t* d_payload, size_t p
                        uint64_t* d_frame_ends_out, void* d_out, int out_dtype, uint32_t* d_status, void* stream)
 {
     if (!c) return TRPX_ERR_BAD_ARG;
-    if (lane < 0 || lane >= N_LANES || !d_payload || !payload_bytes || !d_out || !d_status ||
+    if (lane < 0 || lane >= DEV_LANES || !d_payload || !payload_bytes || !d_out || !d_status ||
         !dtype_size(out_dtype) || !block || !n_values || !n_frames)
         return TRPX_ERR_BAD_ARG;
     if (is_signed && !dtype_signed(out_dtype)) return TRPX_ERR_BAD_ARG;      // Terse.hpp:356-357
@@ -344,9 +375,11 @@ int trpx_decode_device(trpx_ctx* c, int lane, const uint8_t* d_payload, size_t p
 }
 
 // ------------------------------------------------------------------------------ TERSE, host pointers
-// Frames are cut into batches of ~batch_bytes; batch b runs on lane b % N_LANES: H2D, encode, D2H of
-// (frame ends, prolix_bits, status), then -- once its size is known -- D2H of the payload straight to
-// its final place in `out`.  Up to N_LANES batches are in flight, so copies overlap kernels.
+// Frames are cut into batches of ~batch_bytes; batch b runs on lane b % enc_lanes: H2D, encode, then a small
+// kernel stores (frame ends, prolix_bits, status) straight into pinned host memory -- no copy engine, so these few
+// bytes never queue behind another context's bulk D2H traffic.  Once a batch's size is known its payload goes
+// D2H to its final place in `out` on the lane's copy stream; the host never waits for that copy before the call's
+// end (the lane's next kernel waits for it on the device), so the H2D engine is never left idle.
 int trpx_encode_host(trpx_ctx* c, const void* pixels, int dtype, size_t n_values, size_t n_frames, unsigned block,
                      uint8_t* out, size_t out_capacity, size_t* frame_bytes, size_t* total_bytes,
                      unsigned* prolix_bits)
@@ -357,10 +390,11 @@ int trpx_encode_host(trpx_ctx* c, const void* pixels, int dtype, size_t n_values
     std::lock_guard<std::mutex> guard(c->mu);
     cudaSetDevice(c->device);
     const size_t frame_raw = n_values * sz;
-    size_t fpb = c->batch_bytes / (frame_raw ? frame_raw : 1);   // frames per batch
+    size_t fpb = c->enc_batch_bytes / (frame_raw ? frame_raw : 1);   // frames per batch
     if (fpb < 1) fpb = 1;
     if (fpb > n_frames) fpb = n_frames;
     const size_t n_batches = (n_frames + fpb - 1) / fpb;
+    const int nl = c->enc_lanes;
 
     struct Pending { size_t f0, nf; bool active; };
     Pending pend[N_LANES] = {};
@@ -377,18 +411,19 @@ int trpx_encode_host(trpx_ctx* c, const void* pixels, int dtype, size_t n_values
         if (l.h_small[1] != 0) return status_of_device_word(l.h_small[1]);
         const size_t bytes = (size_t)l.h_ends[q.nf - 1];
         if (out_off + bytes > out_capacity) return TRPX_ERR_CAPACITY;
-        if (!cuda_ok(c, cudaMemcpyAsync(out + out_off, l.d_out.p, bytes, cudaMemcpyDeviceToHost, l.stream), "D2H payload"))
+        if (!cuda_ok(c, cudaMemcpyAsync(out + out_off, l.d_out.p, bytes, cudaMemcpyDeviceToHost, l.copy_stream), "D2H payload") ||
+            !cuda_ok(c, cudaEventRecord(l.ev_drained, l.copy_stream), "event record"))
             return TRPX_ERR_CUDA;
+        l.drain_pending = true;
         if (frame_bytes)
             for (size_t i = 0; i < q.nf; ++i) frame_bytes[q.f0 + i] = (size_t)(l.h_ends[i] - (i ? l.h_ends[i - 1] : 0));
         if (l.h_small[0] > pb_max) pb_max = l.h_small[0];
         out_off += bytes;
-        if (!cuda_ok(c, cudaStreamSynchronize(l.stream), "D2H payload")) return TRPX_ERR_CUDA;
         return TRPX_OK;
     };
 
     for (size_t b = 0; b < n_batches && rc == TRPX_OK; ++b) {
-        const int li = (int)(b % N_LANES);
+        const int li = (int)(b % nl);
         Lane& l = c->lanes[li];
         rc = finish(li);
         if (rc != TRPX_OK) break;
@@ -401,24 +436,33 @@ int trpx_encode_host(trpx_ctx* c, const void* pixels, int dtype, size_t n_values
         if (!ensure(c, l.enc_scratch, pl.scratch_bytes)) { rc = TRPX_ERR_NOMEM; break; }
         if (!cuda_ok(c, cudaMemcpyAsync(l.d_in.p, (const uint8_t*)pixels + f0 * frame_raw, nf * frame_raw,
                                         cudaMemcpyHostToDevice, l.stream), "H2D pixels")) { rc = TRPX_ERR_CUDA; break; }
+        if (l.drain_pending) {                                   // d_out still holds the lane's previous payload
+            cudaStreamWaitEvent(l.stream, l.ev_drained, 0);
+            l.drain_pending = false;
+        }
         Launcher L = make_launcher(c, l.stream);
         encode_async(L, dtype, l.d_in.p, n_values, nf, block, l.d_out.p, cap, (u64*)l.d_ends.p, l.d_small, l.d_small + 1,
                      l.enc_scratch.p, pl, enc_ctas_per_sm(c, dtype, pl));
         if (!cuda_ok(c, L.err, "encode launch")) { rc = TRPX_ERR_CUDA; break; }
-        cudaMemcpyAsync(l.h_small, l.d_small, 8, cudaMemcpyDeviceToHost, l.stream);
-        cudaMemcpyAsync(l.h_ends, l.d_ends.p, nf * 8, cudaMemcpyDeviceToHost, l.stream);
+        L.err = launch(publish_results_kernel, (u32)((nf + 255) / 256 < 64 ? (nf + 255) / 256 : 64), 256u, 0, l.stream,
+                       (const u64*)l.d_ends.p, (u64)nf, (const u32*)l.d_small, l.h_ends, l.h_small);
+        L.count("publish_results");
+        if (!cuda_ok(c, L.err, "publish launch")) { rc = TRPX_ERR_CUDA; break; }
         pend[li] = Pending{f0, nf, true};
     }
     // drain in batch order
-    for (size_t k = 0; k < (size_t)N_LANES; ++k) {
-        const int li = (int)((n_batches + k) % N_LANES);
+    for (int k = 0; k < nl; ++k) {
+        const int li = (int)((n_batches + (size_t)k) % (size_t)nl);
         int r = finish(li);
         if (rc == TRPX_OK) rc = r;
     }
-    if (rc != TRPX_OK) {
-        for (int i = 0; i < N_LANES; ++i) cudaStreamSynchronize(c->lanes[i].stream);
-        return rc;
+    for (int i = 0; i < nl; ++i) {
+        Lane& l = c->lanes[i];
+        if (rc != TRPX_OK) cudaStreamSynchronize(l.stream);
+        if (!cuda_ok(c, cudaStreamSynchronize(l.copy_stream), "D2H payload") && rc == TRPX_OK) rc = TRPX_ERR_CUDA;
+        l.drain_pending = false;
     }
+    if (rc != TRPX_OK) return rc;
     if (total_bytes) *total_bytes = out_off;
     if (prolix_bits) *prolix_bits = pb_max;
     return TRPX_OK;
@@ -477,34 +521,40 @@ int trpx_decode_host(trpx_ctx* c, const uint8_t* payload, size_t payload_bytes, 
     if (frame_bytes_out)
         for (size_t f = 0; f < total_frames; ++f) frame_bytes_out[f] = (size_t)(ends[f] - (f ? ends[f - 1] : 0));
 
+    // Batches of ~batch_bytes of output; batch b runs on lane b % dec_lanes: H2D of its payload slab and frame ends,
+    // the kernels, D2H of the pixels.  Nothing here waits on the host: every batch has its own slice of the pinned
+    // frame-end table and its own status word, buffers are reused in stream order, and the call drains once at the end.
     const size_t frame_raw = n_values * so;
     size_t fpb = c->batch_bytes / (frame_raw ? frame_raw : 1);
     if (fpb < 1) fpb = 1;
     if (fpb > n_frames) fpb = n_frames;
     const size_t n_batches = (n_frames + fpb - 1) / fpb;
-    bool active[N_LANES] = {};
+    const int nl = c->dec_lanes;
     int rc = TRPX_OK;
-
-    auto finish = [&](int li) -> int {
-        Lane& l = c->lanes[li];
-        if (!active[li]) return TRPX_OK;
-        active[li] = false;
-        if (!cuda_ok(c, cudaStreamSynchronize(l.stream), "decode batch")) return TRPX_ERR_CUDA;
-        return status_of_device_word(l.h_small[1]);
-    };
+    if (c->h_call_ends_cap < n_frames) {
+        if (c->h_call_ends) cudaFreeHost(c->h_call_ends);
+        c->h_call_ends = nullptr;
+        c->h_call_ends_cap = 0;
+        if (!cuda_ok(c, cudaMallocHost((void**)&c->h_call_ends, (n_frames + 1024) * sizeof(u64)), "cudaMallocHost")) return TRPX_ERR_NOMEM;
+        c->h_call_ends_cap = n_frames + 1024;
+    }
+    if (!ensure(c, c->d_call_status, n_batches * sizeof(u32))) return TRPX_ERR_NOMEM;
+    c->call_status.assign(n_batches, 0);
+    size_t issued = 0;
 
     for (size_t b = 0; b < n_batches && rc == TRPX_OK; ++b) {
-        const int li = (int)(b % N_LANES);
+        const int li = (int)(b % nl);
         Lane& l = c->lanes[li];
-        rc = finish(li);
-        if (rc != TRPX_OK) break;
         const size_t f0 = first_frame + b * fpb, nf = (b * fpb + fpb <= n_frames) ? fpb : n_frames - b * fpb;
         const u64 slab0 = f0 ? ends[f0 - 1] : 0, slab1 = ends[f0 + nf - 1];
         const size_t slab = (size_t)(slab1 - slab0);
         if (slab1 > payload_bytes || slab1 <= slab0) { rc = TRPX_ERR_MALFORMED; break; }
-        if (!ensure(c, l.d_in, slab + 32) || !ensure(c, l.d_out, nf * frame_raw + 16) || !ensure(c, l.d_ends, nf * 8) ||
-            !ensure_host_ends(c, l, nf)) { rc = TRPX_ERR_NOMEM; break; }
-        for (size_t i = 0; i < nf; ++i) l.h_ends[i] = ends[f0 + i] - slab0;
+        if (!ensure(c, l.d_in, slab + 32) || !ensure(c, l.d_out, nf * frame_raw + 16) || !ensure(c, l.d_ends, nf * 8)) {
+            rc = TRPX_ERR_NOMEM;
+            break;
+        }
+        u64* h_ends = c->h_call_ends + b * fpb;
+        for (size_t i = 0; i < nf; ++i) h_ends[i] = ends[f0 + i] - slab0;
         u32 seg, warm, sub_shift;
         walk_geometry(c, slab, nf, (n_values + block - 1) / block, seg, warm, sub_shift);
         DecPlan pl = dec_plan(out_dtype, slab, n_values, nf, block, l.d_out.p, seg, warm, sub_shift);
@@ -512,24 +562,25 @@ int trpx_decode_host(trpx_ctx* c, const uint8_t* payload, size_t payload_bytes, 
         if (!ensure(c, l.dec_scratch, pl.scratch_bytes)) { rc = TRPX_ERR_NOMEM; break; }
         cudaMemsetAsync((uint8_t*)l.d_in.p + (slab & ~(size_t)15), 0, 32, l.stream);   // defined bytes after the slab
         if (!cuda_ok(c, cudaMemcpyAsync(l.d_in.p, payload + slab0, slab, cudaMemcpyHostToDevice, l.stream), "H2D payload") ||
-            !cuda_ok(c, cudaMemcpyAsync(l.d_ends.p, l.h_ends, nf * 8, cudaMemcpyHostToDevice, l.stream), "H2D ends")) {
+            !cuda_ok(c, cudaMemcpyAsync(l.d_ends.p, h_ends, nf * 8, cudaMemcpyHostToDevice, l.stream), "H2D ends")) {
             rc = TRPX_ERR_CUDA;
             break;
         }
         Launcher L = make_launcher(c, l.stream);
         decode_async(L, l.d_in.p, slab, is_signed != 0, block, n_values, nf, (const u64*)l.d_ends.p, nullptr, l.d_out.p,
-                     out_dtype, l.d_small + 1, l.dec_scratch.p, pl, c->coop_grid);
+                     out_dtype, (u32*)c->d_call_status.p + b, l.dec_scratch.p, pl, c->coop_grid);
         if (!cuda_ok(c, L.err, "decode launch")) { rc = TRPX_ERR_CUDA; break; }
         cudaMemcpyAsync((uint8_t*)out + b * fpb * frame_raw, l.d_out.p, nf * frame_raw, cudaMemcpyDeviceToHost, l.stream);
-        cudaMemcpyAsync(l.h_small, l.d_small, 8, cudaMemcpyDeviceToHost, l.stream);
-        active[li] = true;
+        issued = b + 1;
     }
-    for (int li = 0; li < N_LANES; ++li) {
-        int r = finish(li);
-        if (rc == TRPX_OK) rc = r;
+    for (int li = 0; li < nl; ++li)
+        if (!cuda_ok(c, cudaStreamSynchronize(c->lanes[li].stream), "decode batch") && rc == TRPX_OK) rc = TRPX_ERR_CUDA;
+    if (rc == TRPX_OK && issued) {
+        if (!cuda_ok(c, cudaMemcpy(c->call_status.data(), c->d_call_status.p, issued * sizeof(u32), cudaMemcpyDeviceToHost), "D2H status"))
+            return TRPX_ERR_CUDA;
+        for (size_t b = 0; b < issued; ++b)
+            if (c->call_status[b] != 0) return status_of_device_word(c->call_status[b]);
     }
-    if (rc != TRPX_OK)
-        for (int i = 0; i < N_LANES; ++i) cudaStreamSynchronize(c->lanes[i].stream);
     return rc;
 }
 
