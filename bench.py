@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--frames", type=int, default=10000, help="frames per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-chunk", type=int, default=1000,
                     help="frames per chunk of the streamed e2e (encode of chunk k+1 overlaps decode of chunk k)")
     ap.add_argument("--e2e-ramp", type=int, default=0, help="frames of the first and of the last chunk (0: --e2e-chunk)")
@@ -348,7 +348,8 @@ def run_ours(a):
         h_px = torch.empty((F, N_VALUES), dtype=torch.int16, pin_memory=True)
         h_px.copy_(px)
         h_back = torch.empty((F, N_VALUES), dtype=torch.int16, pin_memory=True)
-        h_payload = torch.empty(cbytes + 4096, dtype=torch.uint8, pin_memory=True)
+        pfs = (int(1.25 * cbytes / F) + 255) // 256 * 256           # payload slot bytes per frame of the streamed run
+        h_payload = torch.empty(F * pfs + (F + 2) * 4096, dtype=torch.uint8, pin_memory=True)
         fb = np.zeros(F, np.uint64)
         L = trpx_b200.lib()
         tot = ctypes.c_size_t(0)
@@ -384,9 +385,9 @@ def run_ours(a):
         cuts = [0] + list(range(ramp, F - ramp, chunk)) + ([F - ramp] if F > 2 * ramp else []) + [F]
         cuts = sorted(set(cuts))
         n_chunks = len(cuts) - 1
-        pfs = (int(1.25 * cbytes / F) + 255) // 256 * 256           # payload slot bytes per frame
         slot_off = [cuts[c] * pfs + c * 4096 for c in range(n_chunks)]
-        h_slots = torch.empty(F * pfs + (n_chunks + 1) * 4096, dtype=torch.uint8, pin_memory=True)
+        h_slots = h_payload                                        # (sized for the slots below)
+        assert h_slots.numel() >= F * pfs + (n_chunks + 1) * 4096
 
         trace = []
 
@@ -435,6 +436,8 @@ def run_ours(a):
             return sum(sizes)
 
         def timed(fn):
+            """per-step wall times of 1 warm-up + --e2e-steps timed passes (max over ranks); the median is reported:
+            PCIe throughput on a shared host varies from pass to pass, all passes are listed in the JSON"""
             ts = []
             for k in range(1 + a.e2e_steps):
                 h_back.zero_()
@@ -446,16 +449,16 @@ def run_ours(a):
                 assert nbytes == cbytes and torch.equal(h_back, h_px), "e2e round trip failed"
                 if k:                                              # first pass = warm-up (allocations)
                     ts.append(t1 - t0)
-            t = torch.tensor([sum(ts)], dtype=torch.float64, device=dev)
+            t = torch.tensor(ts, dtype=torch.float64, device=dev)
             if dist is not None:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.cpu()[0]) / len(ts)
+            ts = sorted(float(x) for x in t.cpu())
+            return ts[len(ts) // 2] if len(ts) % 2 else 0.5 * (ts[len(ts) // 2 - 1] + ts[len(ts) // 2]), ts
 
-        seq_s = timed(sequential)
-        str_s = timed(streamed)
+        seq_s, seq_all = timed(sequential)
+        str_s, str_all = timed(streamed)
         for c_ in enc_ctx[1:] + dec_ctx:
             c_.close()
-        del h_slots
         if os.environ.get("TRPX_E2E_TRACE"):
             sys.stderr.write("e2e trace (side, chunk, start ms, end ms): %s\n" % sorted(trace, key=lambda r: r[2]))
         e2e_s = min(seq_s, str_s)
@@ -464,11 +467,14 @@ def run_ours(a):
                "uncompressed_GBps": world * raw_bytes / e2e_s / 1e9,
                "api": "trpx_encode_host + trpx_decode_host (pinned host buffers)",
                "mode": "streamed" if str_s <= seq_s else "sequential",
-               "streamed": {"value": world * F / str_s, "ms_per_step": 1e3 * str_s, "chunk_frames": chunk, "first_last_chunk_frames": ramp,
+               "streamed": {"value": world * F / str_s, "ms_per_step": 1e3 * str_s, "ms_all_steps": [round(1e3 * x, 2) for x in str_all],
+                            "chunk_frames": chunk, "first_last_chunk_frames": ramp,
                             "encoder_threads": n_enc, "decoder_threads": n_dec,
                             "how": "host threads with one context each: chunks are encoded round-robin and decoded as "
                                    "soon as they are encoded, so H2D and D2H overlap (full-duplex PCIe)"},
+               "timing": "median of %d timed passes after one warm-up pass, host clock around the calls" % a.e2e_steps,
                "sequential": {"value": world * F / seq_s, "ms_per_step": 1e3 * seq_s,
+                              "ms_all_steps": [round(1e3 * x, 2) for x in seq_all],
                               "encode_ms": 1e3 * min(p[0] for p in seq_parts[1:]),
                               "decode_ms": 1e3 * min(p[1] for p in seq_parts[1:]),
                               "how": "one call encodes the whole stack, a second one decodes the whole payload"}}

@@ -31,6 +31,7 @@ struct Lane {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // host flavours: payload D2H of the encoder, off the lane's main stream
     cudaEvent_t ev_drained = nullptr;     // ... recorded there once d_out has been copied out
+    cudaEvent_t ev_done = nullptr;        // decoder: the lane's kernels have written d_out
     bool drain_pending = false;
     DevBuf enc_scratch, dec_scratch;   // look-back descriptors / P1 tables
     DevBuf d_in, d_out, d_ends;        // staging of the host-pointer flavours
@@ -133,6 +134,12 @@ void walk_geometry(const trpx_ctx* c, u64 payload_bytes, u64 n_frames, u64 nbloc
     // short segments in bytes -- the same ~2400 blocks -- and therefore enough walkers to fill the machine
     const u64 slice = (u64)256 << (sub_shift - 3);
     u64 sg = (2 * w + slice - 1) / slice * slice;
+    // A walker is one dependent chain over warm-up + segment, and a call whose payload gives fewer segments than
+    // the machine has lanes for (a few big frames, one batch of a host call) is bound by the length of that chain,
+    // not by throughput: then segments shrink towards one slice until ~12 warps of walkers per SM exist.
+    const u64 lanes_wanted = (u64)c->sm_count * 12 * 32;
+    const u64 fit = payload_bytes / lanes_wanted / slice * slice;
+    if (sg > fit) sg = fit;
     if (sg < slice) sg = slice;
     if (!warm) warm = (u32)w;
     if (!seg) seg = (u32)sg;
@@ -240,6 +247,7 @@ int trpx_ctx_create(int device, trpx_ctx** out)
         if (!cuda_ok(c, cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking), "cudaStreamCreate") ||
             !cuda_ok(c, cudaStreamCreateWithFlags(&l.copy_stream, cudaStreamNonBlocking), "cudaStreamCreate") ||
             !cuda_ok(c, cudaEventCreateWithFlags(&l.ev_drained, cudaEventDisableTiming), "cudaEventCreate") ||
+            !cuda_ok(c, cudaEventCreateWithFlags(&l.ev_done, cudaEventDisableTiming), "cudaEventCreate") ||
             !cuda_ok(c, cudaMalloc((void**)&l.d_small, 64), "cudaMalloc") ||
             !cuda_ok(c, cudaMallocHost((void**)&l.h_small, 64), "cudaMallocHost")) {
             trpx_ctx_destroy(c);
@@ -277,6 +285,7 @@ void trpx_ctx_destroy(trpx_ctx* c)
         if (l.stream) { cudaStreamSynchronize(l.stream); cudaStreamDestroy(l.stream); }
         if (l.copy_stream) { cudaStreamSynchronize(l.copy_stream); cudaStreamDestroy(l.copy_stream); }
         if (l.ev_drained) cudaEventDestroy(l.ev_drained);
+        if (l.ev_done) cudaEventDestroy(l.ev_done);
         DevBuf* bufs[] = {&l.enc_scratch, &l.dec_scratch, &l.d_in, &l.d_out, &l.d_ends};
         for (DevBuf* b : bufs)
             if (b->p) cudaFree(b->p);
@@ -566,15 +575,28 @@ int trpx_decode_host(trpx_ctx* c, const uint8_t* payload, size_t payload_bytes, 
             rc = TRPX_ERR_CUDA;
             break;
         }
+        if (l.drain_pending) {                                   // d_out still holds the lane's previous batch
+            cudaStreamWaitEvent(l.stream, l.ev_drained, 0);
+            l.drain_pending = false;
+        }
         Launcher L = make_launcher(c, l.stream);
         decode_async(L, l.d_in.p, slab, is_signed != 0, block, n_values, nf, (const u64*)l.d_ends.p, nullptr, l.d_out.p,
                      out_dtype, (u32*)c->d_call_status.p + b, l.dec_scratch.p, pl, c->coop_grid);
         if (!cuda_ok(c, L.err, "decode launch")) { rc = TRPX_ERR_CUDA; break; }
-        cudaMemcpyAsync((uint8_t*)out + b * fpb * frame_raw, l.d_out.p, nf * frame_raw, cudaMemcpyDeviceToHost, l.stream);
+        // the pixels leave on the lane's copy stream: the lane's next payload upload does not wait for them
+        cudaEventRecord(l.ev_done, l.stream);
+        cudaStreamWaitEvent(l.copy_stream, l.ev_done, 0);
+        cudaMemcpyAsync((uint8_t*)out + b * fpb * frame_raw, l.d_out.p, nf * frame_raw, cudaMemcpyDeviceToHost, l.copy_stream);
+        cudaEventRecord(l.ev_drained, l.copy_stream);
+        l.drain_pending = true;
         issued = b + 1;
     }
-    for (int li = 0; li < nl; ++li)
-        if (!cuda_ok(c, cudaStreamSynchronize(c->lanes[li].stream), "decode batch") && rc == TRPX_OK) rc = TRPX_ERR_CUDA;
+    for (int li = 0; li < nl; ++li) {
+        Lane& l = c->lanes[li];
+        if (!cuda_ok(c, cudaStreamSynchronize(l.stream), "decode batch") && rc == TRPX_OK) rc = TRPX_ERR_CUDA;
+        if (!cuda_ok(c, cudaStreamSynchronize(l.copy_stream), "D2H pixels") && rc == TRPX_OK) rc = TRPX_ERR_CUDA;
+        l.drain_pending = false;
+    }
     if (rc == TRPX_OK && issued) {
         if (!cuda_ok(c, cudaMemcpy(c->call_status.data(), c->d_call_status.p, issued * sizeof(u32), cudaMemcpyDeviceToHost), "D2H status"))
             return TRPX_ERR_CUDA;
