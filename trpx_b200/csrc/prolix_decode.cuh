@@ -369,6 +369,25 @@ TRPX_DEVICE void warp_walk(const DecParams& p, u32* buf, const unsigned short* t
 // but window -> table -> advance.  Phase B walks the segment proper: header count, and the checkpoint bookkeeping
 // inlined (one compare per step against the stream position of the next sub-segment boundary).  Shared memory
 // through window addresses; the block size folded in when it is 12.
+// Header at the low bits of `win`, carried width s -> (header length, new width) for the walk loops.  The two forms
+// that make up almost every header of real data -- '1' (same width) and '0' + 3 bits (widths 0..6) -- are decoded
+// with a handful of ALU operations; only the escape forms (low four bits 1110) go through the shared-memory table.
+TRPX_DEVICE void walk_header(saddr_t tab_a, u32 win, u32 s, u32& hl, u32& s_new)
+{
+#ifdef TRPX_WALK_ARITH
+    const u32 t = win & 15u;
+    if (t != 14u) {
+        const bool same = t & 1u;
+        s_new = same ? s : t >> 1;
+        hl = same ? 1u : 4u;
+        return;
+    }
+#endif
+    const u32 e = lds_u16(tab_a + ((win & (HDR_TAB_ENTRIES - 1)) << 1));
+    s_new = (e & HDR_SAME) ? s : e >> 8;
+    hl = e & 15;
+}
+
 template <bool B12>
 TRPX_DEVICE void warp_walk_ckpt(const DecParams& p, u32* buf, const unsigned short* tab, WalkLane& L, CkptSink& ck)
 {
@@ -409,9 +428,9 @@ TRPX_DEVICE void warp_walk_ckpt(const DecParams& p, u32* buf, const unsigned sho
                             run = run > L.qA - L.q ? L.qA - L.q : run;
                             L.q += run;
                         } else {
-                            const u32 e = lds_u16(tab_a + ((win & (HDR_TAB_ENTRIES - 1)) << 1));
-                            L.s = (e & HDR_SAME) ? L.s : e >> 8;
-                            L.q += (e & 15) + L.s * blk;
+                            u32 hl;
+                            walk_header(tab_a, win, L.s, hl, L.s);
+                            L.q += hl + L.s * blk;
                         }
                     }
                 }
@@ -440,8 +459,8 @@ TRPX_DEVICE void warp_walk_ckpt(const DecParams& p, u32* buf, const unsigned sho
                         L.q += run;
                         L.n += run;
                     } else {
-                        const u32 e = lds_u16(tab_a + ((win & (HDR_TAB_ENTRIES - 1)) << 1));
-                        const u32 s_new = (e & HDR_SAME) ? L.s : e >> 8;
+                        u32 hl, s_new;
+                        walk_header(tab_a, win, L.s, hl, s_new);
                         if (L.q >= q_ck) {                  // this header opens sub-segment next_m (and, rarely, more than one)
                             const u32 rel = L.q - L.qA;
                             do {
@@ -450,7 +469,7 @@ TRPX_DEVICE void warp_walk_ckpt(const DecParams& p, u32* buf, const unsigned sho
                                 q_ck = ck.next_m < ck.subs ? q_ck + sub : 0xffffffffu;
                             } while (L.q >= q_ck);
                         }
-                        L.q += (e & 15) + s_new * blk;
+                        L.q += hl + s_new * blk;
                         L.n += 1;
                         L.s = s_new;
                     }
