@@ -364,30 +364,21 @@ TRPX_DEVICE void warp_walk(const DecParams& p, u32* buf, const unsigned short* t
     }
 }
 
-// The walk kernel's own loop: the steps of warp_walk with no sink, in two phases per round.  Phase A is the
-// speculative warm-up (all lanes of a warp start it together and leave it within a round of each other): nothing
-// but window -> table -> advance.  Phase B walks the segment proper: header count, and the checkpoint bookkeeping
-// inlined (one compare per step against the stream position of the next sub-segment boundary).  Shared memory
-// through window addresses; the block size folded in when it is 12.
-// Header at the low bits of `win`, carried width s -> (header length, new width) for the walk loops.  The two forms
-// that make up almost every header of real data -- '1' (same width) and '0' + 3 bits (widths 0..6) -- are decoded
-// with a handful of ALU operations; only the escape forms (low four bits 1110) go through the shared-memory table.
+// Header at the low bits of `win`, carried width s -> (header length, new width) for the walk loops: one look-up in
+// the shared-memory table.  (Decoding the two common forms -- '1' and '0' + 3 bits -- with ALU operations instead,
+// table only for the escape forms, measured exactly the same walk time: the table LDS is not what bounds a step.)
 TRPX_DEVICE void walk_header(saddr_t tab_a, u32 win, u32 s, u32& hl, u32& s_new)
 {
-#ifdef TRPX_WALK_ARITH
-    const u32 t = win & 15u;
-    if (t != 14u) {
-        const bool same = t & 1u;
-        s_new = same ? s : t >> 1;
-        hl = same ? 1u : 4u;
-        return;
-    }
-#endif
     const u32 e = lds_u16(tab_a + ((win & (HDR_TAB_ENTRIES - 1)) << 1));
     s_new = (e & HDR_SAME) ? s : e >> 8;
     hl = e & 15;
 }
 
+// The walk kernel's own loop: the steps of warp_walk with no sink, in two phases per round.  Phase A is the
+// speculative warm-up (all lanes of a warp start it together and leave it within a round of each other): nothing
+// but window -> table -> advance.  Phase B walks the segment proper: header count, and the checkpoint bookkeeping
+// inlined (one compare per step against the stream position of the next sub-segment boundary).  Shared memory
+// through window addresses; the block size folded in when it is 12.
 template <bool B12>
 TRPX_DEVICE void warp_walk_ckpt(const DecParams& p, u32* buf, const unsigned short* tab, WalkLane& L, CkptSink& ck)
 {
