@@ -102,19 +102,31 @@ class ClockSampler:
 
     def _pump(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.perf_counter(), ln.strip()))
+
+    def begin(self):
+        """the timed region starts now (the sampler itself is started well before: nvidia-smi needs a second or
+        more to come up on an 8-GPU box, longer than the timed region lasts)"""
+        self.t_begin = time.perf_counter()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t_end = time.perf_counter()
         time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        t_begin = getattr(self, "t_begin", 0.0)
+        inside = [ln for t, ln in self.lines if t_begin <= t <= t_end + 0.05]   # (a sample is printed ~ms after it is taken)
+        window = "timed region"
+        if not inside:                                          # region shorter than the sampling period: nearest samples
+            inside = [ln for t, ln in self.lines if t >= t_begin - 0.1][:3] or [ln for t, ln in self.lines][-3:]
+            window = "nearest samples (timed region shorter than the sampling period)"
         sm, smax, reasons, pw = [], [], set(), []
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -129,7 +141,8 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None}
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None,
+                "window": window}
 
 
 # ------------------------------------------------------------------------------------------ CPU baseline
@@ -273,6 +286,8 @@ def run_ours(a):
             dist.barrier(device_ids=[local])
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()                                                 # begin() marks the timed region
     codec = trpx_b200.Codec(local)
     codec.set_profiling(True)
     px = synth_stack(torch, F, 1000 + 100000 * rank, dev)
@@ -310,8 +325,7 @@ def run_ours(a):
     # ---- timed: exactly K steps, CUDA events on the launching stream
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(a.steps)]
     ktimes = {}
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.begin()
     l0 = codec.launches
     t_host0 = time.perf_counter()
     for k in range(a.steps):
@@ -345,12 +359,32 @@ def run_ours(a):
     # ---- e2e: host buffers (pinned), through the host-pointer C ABI; H2D + D2H inside the timed region
     e2e = None
     if not a.no_e2e:
-        h_px = torch.empty((F, N_VALUES), dtype=torch.int16, pin_memory=True)
-        h_px.copy_(px)
-        h_back = torch.empty((F, N_VALUES), dtype=torch.int16, pin_memory=True)
-        pfs = (int(1.25 * cbytes / F) + 255) // 256 * 256           # payload slot bytes per frame of the streamed run
-        h_payload = torch.empty(F * pfs + (F + 2) * 4096, dtype=torch.uint8, pin_memory=True)
-        fb = np.zeros(F, np.uint64)
+        # the whole stack in pinned host memory (11.9 GB per rank at 10,000 frames); should the host refuse that much
+        # (all ranks of a box pin at once), the e2e runs on the first half, quarter ... of the frames and says so
+        Fe = F
+        while True:
+            try:
+                cb_e = int(ends[Fe - 1])
+                pfs = (int(1.25 * cb_e / Fe) + 255) // 256 * 256   # payload slot bytes per frame of the streamed run
+                h_px = torch.empty((Fe, N_VALUES), dtype=torch.int16, pin_memory=True)
+                h_back = torch.empty((Fe, N_VALUES), dtype=torch.int16, pin_memory=True)
+                h_payload = torch.empty(Fe * pfs + (Fe + 2) * 4096, dtype=torch.uint8, pin_memory=True)
+                break
+            except RuntimeError:
+                h_px = h_back = h_payload = None
+                if Fe <= 500:
+                    raise
+                Fe //= 2
+        if dist is not None:                                       # every rank runs the e2e on the same number of frames
+            fe_t = torch.tensor([Fe], dtype=torch.int64, device=dev)
+            dist.all_reduce(fe_t, op=dist.ReduceOp.MIN)
+            if int(fe_t[0]) < Fe:
+                Fe = int(fe_t[0])
+                cb_e = int(ends[Fe - 1])
+                h_px, h_back = h_px[:Fe], h_back[:Fe]
+        raw_e = Fe * N_VALUES * 2
+        h_px.copy_(px[:Fe])
+        fb = np.zeros(Fe, np.uint64)
         L = trpx_b200.lib()
         tot = ctypes.c_size_t(0)
         pb = ctypes.c_uint(0)
@@ -362,11 +396,11 @@ def run_ours(a):
         def sequential():
             """encode the whole stack, then decode the whole payload: two calls on one context"""
             t_a = time.perf_counter()
-            rc = L.trpx_encode_host(codec._h, h_px.data_ptr(), trpx_b200.U16, N_VALUES, F, 12, h_payload.data_ptr(),
+            rc = L.trpx_encode_host(codec._h, h_px.data_ptr(), trpx_b200.U16, N_VALUES, Fe, 12, h_payload.data_ptr(),
                                     h_payload.numel(), fb.ctypes.data, ctypes.byref(tot), ctypes.byref(pb))
             assert rc == 0, rc
             t_b = time.perf_counter()
-            rc = L.trpx_decode_host(codec._h, h_payload.data_ptr(), tot.value, 0, 12, N_VALUES, F, 0, F,
+            rc = L.trpx_decode_host(codec._h, h_payload.data_ptr(), tot.value, 0, 12, N_VALUES, Fe, 0, Fe,
                                     fb.ctypes.data, None, h_back.data_ptr(), trpx_b200.U16)
             assert rc == 0, rc
             seq_parts.append((t_b - t_a, time.perf_counter() - t_b))
@@ -380,14 +414,14 @@ def run_ours(a):
         n_enc, n_dec = max(1, a.e2e_enc_threads), max(1, a.e2e_dec_threads)
         enc_ctx = [codec] + [trpx_b200.Codec(local) for _ in range(n_enc - 1)]
         dec_ctx = [trpx_b200.Codec(local) for _ in range(n_dec)]
-        chunk = max(1, min(F, a.e2e_chunk))
+        chunk = max(1, min(Fe, a.e2e_chunk))
         ramp = max(1, min(chunk, a.e2e_ramp or chunk))             # (a shorter first and last chunk did not pay: DESIGN.md 5)
-        cuts = [0] + list(range(ramp, F - ramp, chunk)) + ([F - ramp] if F > 2 * ramp else []) + [F]
+        cuts = [0] + list(range(ramp, Fe - ramp, chunk)) + ([Fe - ramp] if Fe > 2 * ramp else []) + [Fe]
         cuts = sorted(set(cuts))
         n_chunks = len(cuts) - 1
         slot_off = [cuts[c] * pfs + c * 4096 for c in range(n_chunks)]
         h_slots = h_payload                                        # (sized for the slots below)
-        assert h_slots.numel() >= F * pfs + (n_chunks + 1) * 4096
+        assert h_slots.numel() >= Fe * pfs + (n_chunks + 1) * 4096
 
         trace = []
 
@@ -446,7 +480,7 @@ def run_ours(a):
                 nbytes = fn()
                 torch.cuda.synchronize()
                 t1 = time.perf_counter()
-                assert nbytes == cbytes and torch.equal(h_back, h_px), "e2e round trip failed"
+                assert nbytes == cb_e and torch.equal(h_back, h_px), "e2e round trip failed"
                 if k:                                              # first pass = warm-up (allocations)
                     ts.append(t1 - t0)
             t = torch.tensor(ts, dtype=torch.float64, device=dev)
@@ -462,18 +496,18 @@ def run_ours(a):
         if os.environ.get("TRPX_E2E_TRACE"):
             sys.stderr.write("e2e trace (side, chunk, start ms, end ms): %s\n" % sorted(trace, key=lambda r: r[2]))
         e2e_s = min(seq_s, str_s)
-        e2e = {"value": world * F / e2e_s, "unit": UNIT, "h2d_bytes_per_step": raw_bytes + cbytes + 8 * F,
-               "d2h_bytes_per_step": cbytes + raw_bytes + 16 * F, "ms_per_step": 1e3 * e2e_s,
-               "uncompressed_GBps": world * raw_bytes / e2e_s / 1e9,
-               "api": "trpx_encode_host + trpx_decode_host (pinned host buffers)",
+        e2e = {"value": world * Fe / e2e_s, "unit": UNIT, "h2d_bytes_per_step": raw_e + cb_e + 8 * Fe,
+               "d2h_bytes_per_step": cb_e + raw_e + 16 * Fe, "ms_per_step": 1e3 * e2e_s,
+               "uncompressed_GBps": world * raw_e / e2e_s / 1e9,
+               "frames_per_gpu": Fe, "api": "trpx_encode_host + trpx_decode_host (pinned host buffers)",
                "mode": "streamed" if str_s <= seq_s else "sequential",
-               "streamed": {"value": world * F / str_s, "ms_per_step": 1e3 * str_s, "ms_all_steps": [round(1e3 * x, 2) for x in str_all],
+               "streamed": {"value": world * Fe / str_s, "ms_per_step": 1e3 * str_s, "ms_all_steps": [round(1e3 * x, 2) for x in str_all],
                             "chunk_frames": chunk, "first_last_chunk_frames": ramp,
                             "encoder_threads": n_enc, "decoder_threads": n_dec,
                             "how": "host threads with one context each: chunks are encoded round-robin and decoded as "
                                    "soon as they are encoded, so H2D and D2H overlap (full-duplex PCIe)"},
                "timing": "median of %d timed passes after one warm-up pass, host clock around the calls" % a.e2e_steps,
-               "sequential": {"value": world * F / seq_s, "ms_per_step": 1e3 * seq_s,
+               "sequential": {"value": world * Fe / seq_s, "ms_per_step": 1e3 * seq_s,
                               "ms_all_steps": [round(1e3 * x, 2) for x in seq_all],
                               "encode_ms": 1e3 * min(p[0] for p in seq_parts[1:]),
                               "decode_ms": 1e3 * min(p[1] for p in seq_parts[1:]),

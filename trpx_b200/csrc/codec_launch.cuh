@@ -252,7 +252,7 @@ inline void unpack_launch_t(Launcher& L, const DecPlan& pl, const DecParams& p)
 {
     if (pl.staged) {
         u64 grid = pl.max_segs * div_up(pl.subs_per_seg, UNP_NT);      // slices; persistent CTAs take them round-robin
-        if (grid > (u64)L.sm_count * 3) grid = (u64)L.sm_count * 3;
+        if (grid > (u64)L.sm_count * UNP_CTAS) grid = (u64)L.sm_count * UNP_CTAS;
         L.err = launch(prolix_unpack_seg_kernel<O, SGN>, (u32)grid, (u32)UNP_NT, (size_t)UNP_SMEM_BYTES, L.stream, p);
         L.count("prolix_unpack_seg");
     } else {

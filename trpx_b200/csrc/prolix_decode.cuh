@@ -991,7 +991,13 @@ constexpr u32 UNP_SPAN_WORDS = UNP_NT * (SUB_BYTES / 4) + UNP_TAIL_WORDS + 4;
 // always + UNP_CP.
 constexpr u32 UNP_CP = 288, UNP_ROWS = 20;
 constexpr u32 UNP_SPAN_SMEM_WORDS = UNP_ROWS * UNP_CP;
-constexpr u32 UNP_STAGE_BYTES = 40 * 1024;
+#ifndef UNP_STAGE_KB
+#define UNP_STAGE_KB 40
+#endif
+#ifndef UNP_CTAS
+#define UNP_CTAS 3          // resident CTAs per SM the unpack kernel is sized for (shared memory: stage + span + table)
+#endif
+constexpr u32 UNP_STAGE_BYTES = UNP_STAGE_KB * 1024;
 constexpr u32 UNP_SM_TAB = 64;                           // byte offsets inside dynamic shared memory
 constexpr u32 UNP_SM_SPAN = UNP_SM_TAB + HDR_TAB_BYTES;
 constexpr u32 UNP_SM_STAGE = (UNP_SM_SPAN + UNP_SPAN_SMEM_WORDS * 4 + 127) / 128 * 128;
@@ -1203,7 +1209,7 @@ TRPX_DEVICE void stage_slice(u32* span, u32 span_chunks, const uint4 (&pre)[UNP_
 
 // Persistent CTAs: slice i is unpacked while the stream of slice i+1 and the descriptors of slice i+2 are in flight.
 template <typename O, bool SGN>
-TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, 3) prolix_unpack_seg_kernel(DecParams p)
+TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, UNP_CTAS) prolix_unpack_seg_kernel(DecParams p)
 {
     constexpr u32 SO = sizeof(O);
     constexpr u32 CB = UnpCap<O>::BLOCKS;
