@@ -81,16 +81,58 @@ def synth_stack(torch, frames, seed, dev, chunk=200):
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock, power and throttle reasons of one GPU sampled DURING the timed region: an in-process NVML thread
+    (a sample every ~2 ms, time-stamped), or -- without pynvml -- an `nvidia-smi -lms 20` child process.  Started
+    well before the timed region (NVML / nvidia-smi need up to a second to come up on an 8-GPU box); begin() and
+    stop() bracket the region and only samples taken in between are reported."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, uuid=None):
         self.idx = gpu_index
+        self.uuid = uuid
         self.proc = None
-        self.lines = []
+        self.nvml = None
+        self.samples = []            # (t, sm_mhz, sm_max_mhz, power_w, reasons tuple)
+        self.t_begin = 0.0
+        self.run = False
 
     def start(self):
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            h = None
+            if self.uuid:
+                for u in ("GPU-" + str(self.uuid), str(self.uuid)):
+                    try:
+                        h = N.nvmlDeviceGetHandleByUUID(u.encode() if isinstance(u, str) else u)
+                        break
+                    except Exception:
+                        h = None
+            if h is None:
+                h = N.nvmlDeviceGetHandleByIndex(self.idx)
+            smax = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+
+            def loop():
+                while self.run:
+                    try:
+                        r = int(get_reasons(h))
+                        self.samples.append((time.perf_counter(), float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), smax,
+                                             N.nvmlDeviceGetPowerUsage(h) / 1000.0, tuple(n for n, b in bits if r & b)))
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+
+            self.nvml = N
+            self.run = True
+            self.t = threading.Thread(target=loop, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                                           "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE,
@@ -102,47 +144,45 @@ class ClockSampler:
 
     def _pump(self):
         for ln in self.proc.stdout:
-            self.lines.append((time.perf_counter(), ln.strip()))
-
-    def begin(self):
-        """the timed region starts now (the sampler itself is started well before: nvidia-smi needs a second or
-        more to come up on an 8-GPU box, longer than the timed region lasts)"""
-        self.t_begin = time.perf_counter()
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        t_end = time.perf_counter()
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        t_begin = getattr(self, "t_begin", 0.0)
-        inside = [ln for t, ln in self.lines if t_begin <= t <= t_end + 0.05]   # (a sample is printed ~ms after it is taken)
-        window = "timed region"
-        if not inside:                                          # region shorter than the sampling period: nearest samples
-            inside = [ln for t, ln in self.lines if t >= t_begin - 0.1][:3] or [ln for t, ln in self.lines][-3:]
-            window = "nearest samples (timed region shorter than the sampling period)"
-        sm, smax, reasons, pw = [], [], set(), []
-        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1]))
-                smax.append(float(f[2]))
-                pw.append(float(f[3]))
+                self.samples.append((time.perf_counter(), float(f[1]), float(f[2]), float(f[3]),
+                                     tuple(n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                                              "sw_power_cap"), f[5:9]) if v.lower().startswith("active"))))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None,
-                "window": window}
+
+    def begin(self):
+        self.t_begin = time.perf_counter()
+
+    def stop(self):
+        t_end = time.perf_counter()
+        if self.nvml is not None:
+            self.run = False
+            self.t.join(timeout=1)
+            how = "NVML thread"
+        elif self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+            how = "nvidia-smi -lms 20"
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML and nvidia-smi unavailable"], "samples": 0}
+        inside = [x for x in self.samples if self.t_begin <= x[0] <= t_end + (0.0 if self.nvml is not None else 0.05)]
+        window = "timed region"
+        if not inside:                                          # (nvidia-smi only: region shorter than its period)
+            inside = [x for x in self.samples if x[0] >= self.t_begin - 0.1][:3] or self.samples[-3:]
+            window = "nearest samples"
+        sm = sorted(x[1] for x in inside)
+        reasons = sorted({r for x in inside for r in x[4]})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(x[2] for x in inside) if inside else None,
+                "reasons": reasons, "samples": len(inside), "power_w_max": max(x[3] for x in inside) if inside else None,
+                "window": window, "how": how}
 
 
 # ------------------------------------------------------------------------------------------ CPU baseline
@@ -286,7 +326,11 @@ def run_ours(a):
             dist.barrier(device_ids=[local])
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
+    try:
+        gpu_uuid = torch.cuda.get_device_properties(local).uuid
+    except Exception:
+        gpu_uuid = None
+    sampler = ClockSampler(local, gpu_uuid)
     sampler.start()                                                 # begin() marks the timed region
     codec = trpx_b200.Codec(local)
     codec.set_profiling(True)
