@@ -231,7 +231,17 @@ public:
                 f_decode(tmp.data(), trpx_detail::dtype_of<V>(), first_frame, n_frames);
                 std::copy(tmp.begin(), tmp.end(), begin);
             }
-        } else {                                            // floating point: via 64-bit integers (Terse.hpp:379-383)
+        } else if constexpr (std::is_same_v<V, float> || std::is_same_v<V, double>) {
+            // floating point (Terse.hpp:379-383): the device converts through a 64-bit integer and a double
+            constexpr int code = std::is_same_v<V, float> ? TRPX_F32 : TRPX_F64;
+            if constexpr (trpx_detail::is_raw_pointer<Iterator>) {
+                f_decode(begin, code, first_frame, n_frames);
+            } else {
+                std::vector<V> tmp(n);
+                f_decode(tmp.data(), code, first_frame, n_frames);
+                std::copy(tmp.begin(), tmp.end(), begin);
+            }
+        } else {                                            // other arithmetic types (long double ...): via 64-bit integers on the host
             if (d_signed) {
                 std::vector<std::int64_t> tmp(n);
                 f_decode(tmp.data(), TRPX_I64, first_frame, n_frames);

@@ -48,7 +48,11 @@ enum {
  * (Terse.hpp:265, :294) */
 enum {
     TRPX_U8 = 0, TRPX_U16 = 1, TRPX_U32 = 2, TRPX_U64 = 3,
-    TRPX_I8 = 4, TRPX_I16 = 5, TRPX_I32 = 6, TRPX_I64 = 7
+    TRPX_I8 = 4, TRPX_I16 = 5, TRPX_I32 = 6, TRPX_I64 = 7,
+    /* output types of the DECODER only (the encoder returns TRPX_ERR_BAD_ARG for them): every value goes
+     * through a 64-bit integer and a double, as in Terse::prolix for floating-point iterators
+     * (Terse.hpp:379-383); signed and unsigned streams are both accepted, nothing is clamped */
+    TRPX_F32 = 8, TRPX_F64 = 9
 };
 
 typedef struct trpx_ctx trpx_ctx;   /* one per GPU / per host thread: streams, scratch, pinned staging */
@@ -66,7 +70,7 @@ int trpx_abi_version(void);
 
 /* ---- sizes ------------------------------------------------------------------------------ */
 
-size_t trpx_dtype_size(int dtype);                       /* 1, 2, 4, 8; 0 for an unknown code */
+size_t trpx_dtype_size(int dtype);                       /* 1, 2, 4, 8 (TRPX_F32: 4, TRPX_F64: 8); 0 for an unknown code */
 int trpx_dtype_is_signed(int dtype);
 /* Capacity that always suffices for n_frames frames of n_values each (multiple of 16 bytes).
  * Replaces the reference's worst-case resize (Terse.hpp:502-504), with the App. C7 under-count fixed. */

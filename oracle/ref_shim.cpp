@@ -137,6 +137,8 @@ int ref_prolix(void* handle, void* out, int out_dtype)
 {
     RefHandle* h = static_cast<RefHandle*>(handle);
     if (!h) return -1;
+    if (out_dtype == 8) { h->t->prolix(static_cast<float*>(out), 0); return 0; }    // floating-point iterators,
+    if (out_dtype == 9) { h->t->prolix(static_cast<double*>(out), 0); return 0; }   // Terse.hpp:379-383
     dispatch(out_dtype, [&](auto* tag) {
         using T = std::remove_pointer_t<decltype(tag)>;
         h->t->prolix(static_cast<T*>(out), 0);

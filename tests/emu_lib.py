@@ -73,6 +73,6 @@ def decode(payload, n, frames, is_signed, out_dtype, block=12, frame_ends=None, 
     fe = None if frame_ends is None else np.ascontiguousarray(frame_ends, dtype=np.uint64)
     rc = L.emu_decode(buf.ctypes.data, payload.size, int(is_signed), block, n, frames,
                       None if fe is None else fe.ctypes.data, fe_out.ctypes.data, outb.ctypes.data,
-                      orc.code_of(npdt), st.ctypes.data, seg_bytes, warm_bytes, C.byref(staged), sub_shift)
+                      orc.FLOAT_CODE[npdt] if npdt in orc.FLOAT_CODE else orc.code_of(npdt), st.ctypes.data, seg_bytes, warm_bytes, C.byref(staged), sub_shift)
     assert rc == 0
     return outb.view(npdt).reshape(frames, n).copy(), int(st[0]), bool(staged.value), fe_out

@@ -14,6 +14,8 @@ U8, U16, U32, U64, I8, I16, I32, I64 = range(8)
 NP_OF = {U8: np.uint8, U16: np.uint16, U32: np.uint32, U64: np.uint64,
          I8: np.int8, I16: np.int16, I32: np.int32, I64: np.int64}
 CODE_OF = {np.dtype(v): k for k, v in NP_OF.items()}
+F32, F64 = 8, 9                                                    # decoder OUTPUT types of the CUDA library only
+FLOAT_CODE = {np.dtype(np.float32): F32, np.dtype(np.float64): F64}
 
 
 def code_of(dt):
@@ -128,8 +130,12 @@ def encode_stack(a, block=12):
 
 
 def decode_frame(payload, n, is_signed, out_dtype, block=12):
-    """Oracle decode of one frame -> (values, bytes consumed)."""
+    """Oracle decode of one frame -> (values, bytes consumed).  Floating-point outputs follow Terse.hpp:379-383:
+    every value through a 64-bit integer (signed or unsigned as the stream is) and a double."""
     payload = np.ascontiguousarray(payload, dtype=np.uint8)
+    if not isinstance(out_dtype, int) and np.dtype(out_dtype) in FLOAT_CODE:
+        v, used = decode_frame(payload, n, is_signed, I64 if is_signed else U64, block)
+        return v.astype(np.float64).astype(out_dtype), used
     out = np.zeros(n, NP_OF[out_dtype] if isinstance(out_dtype, int) else out_dtype)
     used = orc().orc_decode_frame(_ptr(payload), payload.size, int(is_signed), block, n, _ptr(out),
                                   code_of(out.dtype))
@@ -183,6 +189,6 @@ def ref_decode_frame(payload, n, is_signed, prolix_bits, out_dtype, block=12):
     h = ref().ref_open(_ptr(payload), payload.size, int(is_signed), block, prolix_bits, n)
     assert h
     out = np.zeros(n, NP_OF[out_dtype] if isinstance(out_dtype, int) else out_dtype)
-    ref().ref_prolix(h, _ptr(out), code_of(out.dtype))
+    ref().ref_prolix(h, _ptr(out), FLOAT_CODE[out.dtype] if out.dtype in FLOAT_CODE else code_of(out.dtype))
     ref().ref_close(h)
     return out

@@ -38,7 +38,10 @@ def test_size_helpers_match_the_oracle():
         for n, block, frames in [(1, 12, 1), (262144, 12, 3), (1000, 7, 2), (18093576, 12, 1)]:
             cap = L.trpx_max_compressed_bytes(n, code, block, frames)
             assert cap % 16 == 0 and cap >= frames * orc.orc().orc_max_frame_bytes(n, code, block)
-    assert L.trpx_dtype_size(9) == 0 and L.trpx_max_compressed_bytes(10, 9, 12, 1) == 0
+    # TRPX_F32 / TRPX_F64 are output types of the decoder only: they have a size, but nothing can be encoded from them
+    assert L.trpx_dtype_size(8) == 4 and L.trpx_dtype_size(9) == 8 and L.trpx_dtype_is_signed(8) == 1
+    assert L.trpx_max_compressed_bytes(10, 8, 12, 1) == 0 and L.trpx_max_compressed_bytes(10, 9, 12, 1) == 0
+    assert L.trpx_dtype_size(10) == 0 and L.trpx_dtype_size(-1) == 0 and L.trpx_max_compressed_bytes(10, 10, 12, 1) == 0
 
 
 def _has_gpu():

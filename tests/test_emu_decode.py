@@ -129,3 +129,18 @@ def test_checkpoint_spacing_is_a_runtime_choice(sub_shift):
     assert roundtrip(dense, seg_bytes=512, warm_bytes=256, sub_shift=sub_shift) is True
     wide = np.stack([orc.kat_fill(orc.U32, 12 * 400, 3 + f) for f in range(2)])
     assert roundtrip(wide, seg_bytes=1024, warm_bytes=512, sub_shift=sub_shift) is True
+
+
+@pytest.mark.parametrize("fdt", [np.float32, np.float64])
+def test_floating_point_outputs(fdt):
+    """Decoder-only output types (Terse.hpp:379-383): through a 64-bit integer and a double, never clamped; staged
+    (block 12) and generic paths, signed and unsigned streams, values past the mantissa of the output type."""
+    rng = np.random.default_rng(8)
+    u16 = np.stack([orc.kat_fill(orc.U16, 12 * 200 + 8, 60 + f) for f in range(3)])
+    assert roundtrip(u16, out_dtype=fdt, seg_bytes=256, warm_bytes=128)
+    i32 = rng.integers(-2 ** 29, 2 ** 29, (2, 12 * 64)).astype(np.int32)
+    i32[0, :48] = 0
+    roundtrip(i32, out_dtype=fdt, seg_bytes=256, warm_bytes=128)
+    u64 = rng.integers(0, 2 ** 62, (2, 12 * 40), dtype=np.uint64)
+    roundtrip(u64, out_dtype=fdt, seg_bytes=512, warm_bytes=256)
+    roundtrip(u16[:, :1001], block=7, out_dtype=fdt, seg_bytes=128, warm_bytes=64)

@@ -348,3 +348,24 @@ def test_two_contexts_stream_chunks_concurrently(codec):
     want, _, _ = orc.encode_stack(st)
     assert np.array_equal(np.concatenate(parts), want)
     assert np.array_equal(np.concatenate([back[k] for k in range(0, 24, 4)]), st)
+
+
+@pytest.mark.parametrize("fdt", [np.float32, np.float64])
+def test_floating_point_outputs(codec, fdt):
+    """TRPX_F32 / TRPX_F64 (decoder outputs only, Terse.hpp:379-383) on the staged and the generic path; the encoder
+    refuses them."""
+    rng = np.random.default_rng(8)
+    st = np.stack([orc.synth_frame(orc.U16, 256, 256, 2.0, 50, 40 + f) for f in range(5)])
+    roundtrip(codec, st, out_dtype=fdt)
+    roundtrip(codec, np.stack([orc.synth_frame(orc.I32, 128, 96, 3.0, 0, 9 + f) for f in range(3)]), out_dtype=fdt)
+    roundtrip(codec, rng.integers(0, 2 ** 62, (2, 12 * 400), dtype=np.uint64), out_dtype=fdt)
+    roundtrip(codec, rng.integers(-2 ** 40, 2 ** 40, (2, 12 * 400)).astype(np.int64), out_dtype=fdt)
+    roundtrip(codec, st[:2, :5001], block=7, out_dtype=fdt)
+    L = trpx_b200.lib()
+    a = np.zeros(24, fdt)
+    out = np.zeros(4096, np.uint8)
+    tot, pb = C.c_size_t(0), C.c_uint(0)
+    rc = L.trpx_encode_host(codec._h, a.ctypes.data, trpx_b200.dtype_code(fdt), 24, 1, 12, out.ctypes.data, out.size, None,
+                            C.byref(tot), C.byref(pb))
+    assert rc == trpx_b200.ERR_BAD_ARG
+    assert L.trpx_max_compressed_bytes(24, trpx_b200.dtype_code(fdt), 12, 1) == 0

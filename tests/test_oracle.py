@@ -118,3 +118,20 @@ def test_reference_decodes_oracle_streams_with_clamp():
     p, pb = orc.encode_frame(a)
     assert np.array_equal(orc.ref_decode_frame(p, 12, False, pb, np.uint8),
                           orc.decode_frame(p, 12, False, np.uint8)[0])
+
+
+@pytest.mark.parametrize("fdt", [np.float32, np.float64])
+def test_floating_point_outputs_follow_the_reference(fdt):
+    """Terse.hpp:379-383: a floating-point iterator receives double(int64/uint64(field)).  Checked against the live
+    reference where it was built (oracle/_ref), inside its parity domain (values below 2^31: its wide reads are
+    undefined beyond)."""
+    if orc.ref() is None:
+        pytest.skip("oracle/_ref not built (no reference mount)")
+    rng = np.random.default_rng(3)
+    for dt, lo, hi in ((np.uint16, 0, 60000), (np.int16, -3000, 3000), (np.uint32, 0, 2 ** 30), (np.int32, -2 ** 27, 2 ** 27)):
+        a = rng.integers(lo, hi, 12 * 40 + 5).astype(dt)
+        a[24:60] = 0
+        p, pb = orc.ref_encode_frame(a)
+        want = orc.ref_decode_frame(p, a.size, a.dtype.kind == "i", pb, fdt)
+        got, _ = orc.decode_frame(p, a.size, a.dtype.kind == "i", fdt)
+        assert np.array_equal(got, want) and np.array_equal(want, a.astype(np.float64).astype(fdt))

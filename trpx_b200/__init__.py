@@ -11,9 +11,9 @@ import numpy as np
 
 from . import build as _build
 
-U8, U16, U32, U64, I8, I16, I32, I64 = range(8)
+U8, U16, U32, U64, I8, I16, I32, I64, F32, F64 = range(10)      # F32 / F64: decoder outputs only
 _NP = {U8: np.uint8, U16: np.uint16, U32: np.uint32, U64: np.uint64,
-       I8: np.int8, I16: np.int16, I32: np.int32, I64: np.int64}
+       I8: np.int8, I16: np.int16, I32: np.int32, I64: np.int64, F32: np.float32, F64: np.float64}
 _CODE = {np.dtype(v): k for k, v in _NP.items()}
 
 OK, ERR_BAD_ARG, ERR_CAPACITY, ERR_CUDA, ERR_MALFORMED, ERR_NO_DEVICE, ERR_NOMEM = range(7)

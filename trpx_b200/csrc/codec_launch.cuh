@@ -15,10 +15,12 @@ namespace trpx {
 using ::emu::cudaMemsetAsync;
 #endif
 
-enum { DT_U8 = 0, DT_U16, DT_U32, DT_U64, DT_I8, DT_I16, DT_I32, DT_I64 };
+// pixel types 0..7; DT_F32 / DT_F64 only as OUTPUT types of the decoder (Terse.hpp:379-383)
+enum { DT_U8 = 0, DT_U16, DT_U32, DT_U64, DT_I8, DT_I16, DT_I32, DT_I64, DT_F32, DT_F64 };
 
-inline size_t dtype_size(int dt) { return dt < 0 || dt > 7 ? 0 : (size_t)1 << (dt & 3); }
-inline bool dtype_signed(int dt) { return dt >= DT_I8; }
+inline size_t dtype_size(int dt) { return dt < 0 || dt > DT_F64 ? 0 : dt == DT_F32 ? 4 : dt == DT_F64 ? 8 : (size_t)1 << (dt & 3); }
+inline bool dtype_signed(int dt) { return dt >= DT_I8; }                 // (floating point takes signed streams)
+inline bool dtype_is_pixel(int dt) { return dt >= 0 && dt <= DT_I64; }  // what the encoder accepts
 
 #ifndef ENC_NT_U16
 #define ENC_NT_U16 192
@@ -271,6 +273,8 @@ inline void unpack_launch(Launcher& L, int out_dtype, const DecPlan& pl, const D
     case DT_I8: unpack_launch_t<int8_t, SGN>(L, pl, p); break;
     case DT_I16: unpack_launch_t<int16_t, SGN>(L, pl, p); break;
     case DT_I32: unpack_launch_t<int32_t, SGN>(L, pl, p); break;
+    case DT_F32: unpack_launch_t<float, SGN>(L, pl, p); break;
+    case DT_F64: unpack_launch_t<double, SGN>(L, pl, p); break;
     default: unpack_launch_t<int64_t, SGN>(L, pl, p); break;
     }
 }

@@ -850,6 +850,12 @@ struct BitSource {
 
 // Bit_range::get_range semantics (Bit_pointer.hpp:742-792): sign-extend signed streams from bit
 // s-1; a block wider than the output type is clamped to the type's range, else truncated.
+template <typename O> struct IsFloat { static constexpr bool V = false; };
+template <> struct IsFloat<float> { static constexpr bool V = true; };
+template <> struct IsFloat<double> { static constexpr bool V = true; };
+
+// Floating-point outputs go through a 64-bit integer and a double (Terse.hpp:379-383: `begin[i] =
+// double(std::int64_t(bitr))`, unsigned streams through std::uint64_t), never clamped.
 template <typename O, bool SGN>
 TRPX_DEVICE O convert_value(u64 raw, u32 s)
 {
@@ -857,6 +863,7 @@ TRPX_DEVICE O convert_value(u64 raw, u32 s)
     constexpr bool OS = O(-1) < O(0);
     u64 v = raw;
     if (SGN && s < 64 && ((v >> (s - 1)) & 1)) v |= ~0ull << s;
+    if (IsFloat<O>::V) return (O)(SGN ? (double)(i64)v : (double)v);
     if (s > WO) {
         if (!OS) {
             const u64 hi = WO == 64 ? ~0ull : ((1ull << WO) - 1);
@@ -1113,7 +1120,7 @@ TRPX_DEVICE void unpack_block12(const u32* sp, saddr_t col_a, u32 rel, u32 pos, 
         }
         return;
     }
-    if (SO == 4 && s <= 32 && in_rows) {
+    if (SO == 4 && !IsFloat<O>::V && s <= 32 && in_rows) {
         const u32 m = low_mask(s);
         u32 o[12];
 #pragma unroll

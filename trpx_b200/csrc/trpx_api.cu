@@ -220,7 +220,7 @@ int trpx_dtype_is_signed(int dtype) { return dtype_signed(dtype) ? 1 : 0; }
 
 size_t trpx_max_compressed_bytes(size_t n_values, int dtype, unsigned block, size_t n_frames)
 {
-    const size_t sz = dtype_size(dtype);
+    const size_t sz = dtype_is_pixel(dtype) ? dtype_size(dtype) : 0;
     if (!sz || !block) return 0;
     const size_t w = 8 * sz + (dtype_signed(dtype) ? 1 : 0);
     const size_t nblocks = (n_values + block - 1) / block;
@@ -343,7 +343,7 @@ int trpx_encode_device(trpx_ctx* c, int lane, const void* d_pixels, int dtype, s
 {
     if (!c) return TRPX_ERR_BAD_ARG;
     if (lane < 0 || lane >= DEV_LANES || !d_pixels || !d_out || !d_frame_ends || !d_prolix_bits || !d_status ||
-        !dtype_size(dtype) || !block || !n_values || !n_frames)
+        !dtype_is_pixel(dtype) || !block || !n_values || !n_frames)
         return TRPX_ERR_BAD_ARG;
     if (((uintptr_t)d_out & 15) || ((uintptr_t)d_pixels & (dtype_size(dtype) - 1))) return TRPX_ERR_BAD_ARG;
     cudaSetDevice(c->device);
@@ -394,7 +394,7 @@ int trpx_encode_host(trpx_ctx* c, const void* pixels, int dtype, size_t n_values
                      unsigned* prolix_bits)
 {
     if (!c) return TRPX_ERR_BAD_ARG;
-    const size_t sz = dtype_size(dtype);
+    const size_t sz = dtype_is_pixel(dtype) ? dtype_size(dtype) : 0;
     if (!pixels || !out || !sz || !block || !n_values || !n_frames) return TRPX_ERR_BAD_ARG;
     std::lock_guard<std::mutex> guard(c->mu);
     cudaSetDevice(c->device);
