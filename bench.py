@@ -513,6 +513,51 @@ def run_ours(a):
             assert not err, err
             return sum(sizes)
 
+        # Overlapped: ONE trpx_encode_host call for the whole stack (a single uninterrupted upload pipeline); a second
+        # host thread follows trpx_ctx_encode_progress() and decodes, on its own context, whatever prefix of the stack
+        # has landed since its last call (at least --e2e-chunk frames unless the encoder has finished).
+        def overlapped():
+            err = []
+            seq0 = codec.encode_progress()[0]
+            enc_done = threading.Event()
+
+            def enc_side():
+                t_, p_ = ctypes.c_size_t(0), ctypes.c_uint(0)
+                rc = L.trpx_encode_host(codec._h, h_px.data_ptr(), trpx_b200.U16, N_VALUES, Fe, 12, h_payload.data_ptr(),
+                                        h_payload.numel(), fb.ctypes.data, ctypes.byref(t_), ctypes.byref(p_))
+                if rc != 0:
+                    err.append(("encode", rc))
+                tot.value = t_.value
+                enc_done.set()
+
+            def dec_side():
+                f_prev = b_prev = 0
+                while f_prev < Fe and not err:
+                    finished = enc_done.is_set()
+                    seq, f_now, b_now = codec.encode_progress()
+                    if seq == seq0:
+                        f_now = b_now = 0                          # the encode call has not started yet
+                    if f_now - f_prev >= chunk or (finished and f_now > f_prev):
+                        nf = f_now - f_prev
+                        rc = L.trpx_decode_host(dec_ctx[0]._h, h_payload.data_ptr() + b_prev, b_now - b_prev, 0, 12,
+                                                N_VALUES, nf, 0, nf, fb.ctypes.data + 8 * f_prev, None,
+                                                h_back.data_ptr() + f_prev * frame_raw, trpx_b200.U16)
+                        if rc != 0:
+                            err.append(("decode", f_prev, rc))
+                        f_prev, b_prev = f_now, b_now
+                    elif finished and f_now == f_prev:
+                        err.append(("stalled", f_prev))
+                    else:
+                        time.sleep(0.0002)
+
+            th = [threading.Thread(target=enc_side), threading.Thread(target=dec_side)]
+            for t_ in th:
+                t_.start()
+            for t_ in th:
+                t_.join()
+            assert not err, err
+            return tot.value
+
         def timed(fn):
             """per-step wall times of 1 warm-up + --e2e-steps timed passes (max over ranks); the median is reported:
             PCIe throughput on a shared host varies from pass to pass, all passes are listed in the JSON"""
@@ -535,16 +580,21 @@ def run_ours(a):
 
         seq_s, seq_all = timed(sequential)
         str_s, str_all = timed(streamed)
+        ovl_s, ovl_all = timed(overlapped)
         for c_ in enc_ctx[1:] + dec_ctx:
             c_.close()
         if os.environ.get("TRPX_E2E_TRACE"):
             sys.stderr.write("e2e trace (side, chunk, start ms, end ms): %s\n" % sorted(trace, key=lambda r: r[2]))
-        e2e_s = min(seq_s, str_s)
+        e2e_s = min(seq_s, str_s, ovl_s)
         e2e = {"value": world * Fe / e2e_s, "unit": UNIT, "h2d_bytes_per_step": raw_e + cb_e + 8 * Fe,
                "d2h_bytes_per_step": cb_e + raw_e + 16 * Fe, "ms_per_step": 1e3 * e2e_s,
                "uncompressed_GBps": world * raw_e / e2e_s / 1e9,
                "frames_per_gpu": Fe, "api": "trpx_encode_host + trpx_decode_host (pinned host buffers)",
-               "mode": "streamed" if str_s <= seq_s else "sequential",
+               "mode": "overlapped" if ovl_s <= min(seq_s, str_s) else "streamed" if str_s <= seq_s else "sequential",
+               "overlapped": {"value": world * Fe / ovl_s, "ms_per_step": 1e3 * ovl_s,
+                              "ms_all_steps": [round(1e3 * x, 2) for x in ovl_all], "min_decode_frames": chunk,
+                              "how": "one trpx_encode_host call for the whole stack; a second host thread follows "
+                                     "trpx_ctx_encode_progress() and decodes the finished prefix on its own context"},
                "streamed": {"value": world * Fe / str_s, "ms_per_step": 1e3 * str_s, "ms_all_steps": [round(1e3 * x, 2) for x in str_all],
                             "chunk_frames": chunk, "first_last_chunk_frames": ramp,
                             "encoder_threads": n_enc, "decoder_threads": n_dec,

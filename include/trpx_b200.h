@@ -88,6 +88,14 @@ int trpx_encode_host(trpx_ctx* ctx, const void* pixels, int dtype, size_t n_valu
                      unsigned block, uint8_t* out, size_t out_capacity, size_t* frame_bytes,
                      size_t* total_bytes, unsigned* prolix_bits);
 
+/* Progress of the trpx_encode_host call that is running (or ran last) on `ctx`; callable from ANOTHER host thread
+ * while that call runs (it takes no lock the call holds).  The first *frames_done frames are complete: their
+ * payload -- *payload_bytes_done bytes from the start of `out` -- and their frame_bytes[] entries have landed in
+ * the caller's buffers, so a consumer (a file writer, a decoder on another context) can start on them while the
+ * rest of the stack is still being uploaded and encoded.  *call_seq counts the trpx_encode_host calls started on
+ * the context: a consumer reads it before it launches the call and ignores progress until it has changed. */
+int trpx_ctx_encode_progress(trpx_ctx* ctx, size_t* call_seq, size_t* frames_done, size_t* payload_bytes_done);
+
 /* Device-pointer flavour: everything resident in HBM, asynchronous on `stream` (a cudaStream_t).
  *   d_pixels       16-byte aligned
  *   d_out          16-byte aligned, out_capacity >= trpx_max_compressed_bytes() recommended

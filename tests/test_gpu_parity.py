@@ -369,3 +369,43 @@ def test_floating_point_outputs(codec, fdt):
                             C.byref(tot), C.byref(pb))
     assert rc == trpx_b200.ERR_BAD_ARG
     assert L.trpx_max_compressed_bytes(24, trpx_b200.dtype_code(fdt), 12, 1) == 0
+
+
+def test_encode_progress_is_a_consistent_prefix(monkeypatch):
+    """trpx_ctx_encode_progress from a second thread while trpx_encode_host runs (one frame per batch): the reported
+    prefix only grows, its payload bytes are the oracle's prefix bytes, and it ends at the whole stack."""
+    import threading
+    monkeypatch.setenv("TRPX_BATCH_MB", "0")
+    c = trpx_b200.Codec(0)
+    try:
+        st = np.stack([orc.synth_frame(orc.U16, 128, 128, 2.0, 20, 900 + f) for f in range(60)])
+        want, per, _ = orc.encode_stack(st)
+        cum = np.concatenate([[0], np.cumsum(per)]).astype(np.int64)
+        L = trpx_b200.lib()
+        F, N = st.shape
+        cap = L.trpx_max_compressed_bytes(N, trpx_b200.U16, 12, F)
+        out = np.zeros(cap, np.uint8)
+        fb = np.zeros(F, np.uint64)
+        tot, pb = C.c_size_t(0), C.c_uint(0)
+        seq0 = c.encode_progress()[0]
+        seen, stop = [], threading.Event()
+
+        def watcher():
+            while not stop.is_set():
+                q, f, b = c.encode_progress()
+                if q != seq0:
+                    seen.append((f, b, bytes(out[:b]) == bytes(want[:b]), np.array_equal(fb[:f], per[:f])))
+
+        th = threading.Thread(target=watcher)
+        th.start()
+        rc = L.trpx_encode_host(c._h, st.ctypes.data, trpx_b200.U16, N, F, 12, out.ctypes.data, cap, fb.ctypes.data,
+                                C.byref(tot), C.byref(pb))
+        stop.set()
+        th.join()
+        assert rc == 0 and tot.value == want.size
+        assert c.encode_progress()[1:] == (F, want.size)
+        assert seen and all(ok1 and ok2 for _, _, ok1, ok2 in seen)
+        assert all(a[0] <= b[0] and a[1] <= b[1] for a, b in zip(seen, seen[1:]))
+        assert all(b == cum[f] for f, b, _, _ in seen)
+    finally:
+        c.close()

@@ -22,7 +22,7 @@ EXPORTS = ["trpx_abi_version", "trpx_strerror", "trpx_dtype_size", "trpx_dtype_i
            "trpx_max_compressed_bytes", "trpx_ctx_create", "trpx_ctx_destroy", "trpx_ctx_device",
            "trpx_last_error", "trpx_ctx_lanes", "trpx_ctx_launch_count", "trpx_ctx_scratch_bytes",
            "trpx_encode_host", "trpx_encode_device", "trpx_decode_host", "trpx_decode_device",
-           "trpx_ctx_set_profiling", "trpx_ctx_last_kernel_times"]
+           "trpx_ctx_set_profiling", "trpx_ctx_last_kernel_times", "trpx_ctx_encode_progress"]
 
 
 class TrpxError(RuntimeError):
@@ -82,6 +82,8 @@ def lib(build_if_missing=True):
     L.trpx_ctx_set_profiling.argtypes = [vp, i]
     L.trpx_ctx_last_kernel_times.restype = i
     L.trpx_ctx_last_kernel_times.argtypes = [vp, i, C.POINTER(C.c_char_p), C.POINTER(C.c_float), i]
+    L.trpx_ctx_encode_progress.restype = i
+    L.trpx_ctx_encode_progress.argtypes = [vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]
     L.trpx_encode_host.restype = i
     L.trpx_encode_host.argtypes = [vp, vp, i, sz, sz, u, vp, sz, vp, C.POINTER(sz), C.POINTER(u)]
     L.trpx_encode_device.restype = i
@@ -127,6 +129,12 @@ class Codec:
     @property
     def launches(self):
         return int(lib().trpx_ctx_launch_count(self._h))
+
+    def encode_progress(self):
+        """(calls started, frames done, payload bytes done) of the running / last host-pointer encode; any thread."""
+        q, f, b = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+        self._check(lib().trpx_ctx_encode_progress(self._h, C.byref(q), C.byref(f), C.byref(b)))
+        return q.value, f.value, b.value
 
     def set_profiling(self, on=True):
         self._check(lib().trpx_ctx_set_profiling(self._h, int(on)))

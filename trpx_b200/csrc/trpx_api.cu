@@ -6,6 +6,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -46,6 +47,33 @@ struct Lane {
     size_t ev_used = 0;
 };
 
+// Progress of a trpx_encode_host call, readable from another host thread while the call runs: batches whose
+// payload (and frame sizes) have landed in the caller's buffers, as a prefix of the stack.  Advanced by host
+// functions enqueued behind each batch's payload D2H (cudaLaunchHostFunc), read through atomics only.
+struct EncProgress;
+struct EncProgressMark { EncProgress* pr; size_t batch; };
+struct EncProgress {
+    std::atomic<size_t> seq{0}, frames{0}, bytes{0};
+    std::mutex m;
+    std::vector<char> done;
+    std::vector<size_t> cum_frames, cum_bytes;
+    std::vector<EncProgressMark> marks;
+    size_t next = 0;
+};
+
+void CUDART_CB enc_progress_cb(void* arg)
+{
+    EncProgressMark* mk = (EncProgressMark*)arg;
+    EncProgress& pr = *mk->pr;
+    std::lock_guard<std::mutex> g(pr.m);
+    pr.done[mk->batch] = 1;
+    while (pr.next < pr.done.size() && pr.done[pr.next]) {
+        pr.bytes.store(pr.cum_bytes[pr.next], std::memory_order_relaxed);
+        pr.frames.store(pr.cum_frames[pr.next], std::memory_order_release);
+        ++pr.next;
+    }
+}
+
 }  // namespace
 
 struct trpx_ctx {
@@ -63,6 +91,7 @@ struct trpx_ctx {
     u64* h_call_ends = nullptr;        // pinned: frame ends of every batch of one trpx_decode_host call
     size_t h_call_ends_cap = 0;
     DevBuf d_call_status;              // one status word per batch of a trpx_decode_host call
+    EncProgress enc_progress;
     std::vector<u32> call_status;
     u32 coop_grid = 0;
     bool profiling = false;
@@ -314,6 +343,17 @@ size_t trpx_ctx_scratch_bytes(const trpx_ctx* c)
     return t;
 }
 
+int trpx_ctx_encode_progress(trpx_ctx* c, size_t* call_seq, size_t* frames_done, size_t* payload_bytes_done)
+{
+    if (!c) return TRPX_ERR_BAD_ARG;
+    EncProgress& pr = c->enc_progress;
+    std::lock_guard<std::mutex> g(pr.m);                    // (the marks advance under the same lock: a consistent pair)
+    if (call_seq) *call_seq = pr.seq.load(std::memory_order_acquire);
+    if (frames_done) *frames_done = pr.frames.load(std::memory_order_acquire);
+    if (payload_bytes_done) *payload_bytes_done = pr.bytes.load(std::memory_order_acquire);
+    return TRPX_OK;
+}
+
 int trpx_ctx_set_profiling(trpx_ctx* c, int on)
 {
     if (!c) return TRPX_ERR_BAD_ARG;
@@ -405,11 +445,23 @@ int trpx_encode_host(trpx_ctx* c, const void* pixels, int dtype, size_t n_values
     const size_t n_batches = (n_frames + fpb - 1) / fpb;
     const int nl = c->enc_lanes;
 
-    struct Pending { size_t f0, nf; bool active; };
+    struct Pending { size_t f0, nf, batch; bool active; };
     Pending pend[N_LANES] = {};
     size_t out_off = 0;
     unsigned pb_max = 0;
     int rc = TRPX_OK;
+    EncProgress& pr = c->enc_progress;
+    {
+        std::lock_guard<std::mutex> g(pr.m);
+        pr.done.assign(n_batches, 0);
+        pr.cum_frames.assign(n_batches, 0);
+        pr.cum_bytes.assign(n_batches, 0);
+        pr.marks.resize(n_batches);
+        pr.next = 0;
+        pr.frames.store(0, std::memory_order_relaxed);
+        pr.bytes.store(0, std::memory_order_relaxed);
+        pr.seq.fetch_add(1, std::memory_order_release);
+    }
 
     auto finish = [&](int li) -> int {
         Lane& l = c->lanes[li];
@@ -428,6 +480,10 @@ int trpx_encode_host(trpx_ctx* c, const void* pixels, int dtype, size_t n_values
             for (size_t i = 0; i < q.nf; ++i) frame_bytes[q.f0 + i] = (size_t)(l.h_ends[i] - (i ? l.h_ends[i - 1] : 0));
         if (l.h_small[0] > pb_max) pb_max = l.h_small[0];
         out_off += bytes;
+        pr.cum_frames[q.batch] = q.f0 + q.nf;               // (frame_bytes[] above is written before the mark can fire)
+        pr.cum_bytes[q.batch] = out_off;
+        pr.marks[q.batch] = EncProgressMark{&pr, q.batch};
+        cudaLaunchHostFunc(l.copy_stream, enc_progress_cb, &pr.marks[q.batch]);
         return TRPX_OK;
     };
 
@@ -457,7 +513,7 @@ int trpx_encode_host(trpx_ctx* c, const void* pixels, int dtype, size_t n_values
                        (const u64*)l.d_ends.p, (u64)nf, (const u32*)l.d_small, l.h_ends, l.h_small);
         L.count("publish_results");
         if (!cuda_ok(c, L.err, "publish launch")) { rc = TRPX_ERR_CUDA; break; }
-        pend[li] = Pending{f0, nf, true};
+        pend[li] = Pending{f0, nf, b, true};
     }
     // drain in batch order
     for (int k = 0; k < nl; ++k) {
