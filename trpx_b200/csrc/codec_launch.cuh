@@ -186,7 +186,10 @@ inline void encode_async(Launcher& L, int dtype, const void* d_pixels, u64 n_val
 }
 
 // ---------------------------------------------------------------------------------- decode
-constexpr int WALK_NT = 128;      // threads per CTA of the P1 walkers (one stream segment per thread)
+#ifndef TRPX_WALK_NT
+#define TRPX_WALK_NT 256
+#endif
+constexpr int WALK_NT = TRPX_WALK_NT;      // threads per CTA of the P1 walkers (one stream segment per thread)
 constexpr int RESOLVE_NT = 256;   // threads per CTA of the cooperative verify / scan kernel
 constexpr int SEGTAB_NT = 1024;
 
