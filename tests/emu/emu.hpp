@@ -34,24 +34,35 @@ struct Fiber {
     char* stack = nullptr;
     bool done = false;
     ThreadCtx tc{};
+    int slot = 0;                         // which resident CTA the fiber belongs to
 };
 
-struct State {
-    std::vector<Fiber> fibers;
-    ucontext_t sched;
-    int current = -1;
+// One resident CTA: its barriers, warp exchange slots and shared memory.  Several CTAs of a grid are resident at
+// once (EMU_CTAS, default 1) and their fibers are interleaved, so that look-backs, tickets and hand-offs BETWEEN
+// CTAs run concurrently as on the device.
+struct Block {
     uint32_t bar_count = 0, bar_gen = 0;
     uint32_t nbar_count[16] = {0}, nbar_gen[16] = {0};   // named barriers (bar.sync id, n)
     std::vector<uint32_t> wbar_count, wbar_gen;
     std::vector<uint64_t> xch;            // 32 slots per warp
     unsigned char* smem = nullptr;
+    uint32_t alive = 0;
+    bool active = false;
+};
+
+struct State {
+    std::vector<Fiber> fibers;            // slot * block_dim + tid
+    std::vector<Block> blocks;
+    ucontext_t sched;
+    int current = -1;
     const std::function<void()>* body = nullptr;
     uint64_t yields_without_progress = 0;
 };
 
 inline State& S() { static State s; return s; }
 inline ThreadCtx& cur() { return S().fibers[S().current].tc; }
-inline unsigned char* dyn_smem() { return S().smem; }
+inline Block& blk() { return S().blocks[S().fibers[S().current].slot]; }
+inline unsigned char* dyn_smem() { return blk().smem; }
 
 inline void yield()
 {
@@ -64,7 +75,7 @@ inline void trap() { fprintf(stderr, "emu: trap() in block %u thread %u\n", cur(
 
 inline void sync_block()
 {
-    State& s = S();
+    Block& s = blk();
     uint32_t gen = s.bar_gen;
     if (++s.bar_count == cur().block_dim) { s.bar_count = 0; ++s.bar_gen; progress(); }
     else while (s.bar_gen == gen) yield();
@@ -72,7 +83,7 @@ inline void sync_block()
 
 inline void bar_sync(uint32_t id, uint32_t n)
 {
-    State& s = S();
+    Block& s = blk();
     uint32_t gen = s.nbar_gen[id & 15];
     if (++s.nbar_count[id & 15] == n) { s.nbar_count[id & 15] = 0; ++s.nbar_gen[id & 15]; progress(); }
     else while (s.nbar_gen[id & 15] == gen) yield();
@@ -80,13 +91,13 @@ inline void bar_sync(uint32_t id, uint32_t n)
 
 inline void bar_arrive(uint32_t id, uint32_t n)
 {
-    State& s = S();
+    Block& s = blk();
     if (++s.nbar_count[id & 15] == n) { s.nbar_count[id & 15] = 0; ++s.nbar_gen[id & 15]; progress(); }
 }
 
 inline void sync_warp()
 {
-    State& s = S();
+    Block& s = blk();
     uint32_t w = cur().tid >> 5;
     uint32_t lanes = cur().block_dim - w * 32 < 32 ? cur().block_dim - w * 32 : 32;
     uint32_t gen = s.wbar_gen[w];
@@ -96,7 +107,7 @@ inline void sync_warp()
 
 inline uint64_t shfl(uint64_t v, int src)
 {
-    State& s = S();
+    Block& s = blk();
     uint32_t t = cur().tid, w = t >> 5;
     s.xch[w * 32 + (t & 31)] = v;
     sync_warp();
@@ -116,7 +127,7 @@ inline uint64_t shfl_down(uint64_t v, int d)
 }
 inline uint32_t ballot(bool p)
 {
-    State& s = S();
+    Block& s = blk();
     uint32_t t = cur().tid, w = t >> 5;
     s.xch[w * 32 + (t & 31)] = p ? 1 : 0;
     sync_warp();
@@ -128,7 +139,7 @@ inline uint32_t ballot(bool p)
 }
 inline uint32_t warp_reduce(uint32_t v, int op)
 {
-    State& s = S();
+    Block& s = blk();
     uint32_t t = cur().tid, w = t >> 5;
     s.xch[w * 32 + (t & 31)] = v;
     sync_warp();
@@ -168,10 +179,20 @@ inline void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes)
     b->arrived++;
     mbar_check(b);
 }
-inline void mbar_wait(unsigned long long* bar, uint32_t parity)
+inline void mbar_wait(unsigned long long* bar, uint32_t parity, uint32_t code = 0)
 {
     MBar* b = (MBar*)bar;
-    while ((uint32_t)b->phase == (parity & 1)) yield();   // phase flips when the awaited phase completes
+    uint64_t n = 0;
+    while ((uint32_t)b->phase == (parity & 1)) {             // phase flips when the awaited phase completes
+        if (++n == (1u << 16) && getenv("EMU_TRACE"))
+            fprintf(stderr, "emu: long mbarrier wait: bid %u tid %u code %u (warp %u, round %u)\n", cur().bid, cur().tid, code & 15, (code >> 4) & 31, code >> 12);
+        yield();
+    }
+}
+inline bool mbar_test(unsigned long long* bar, uint32_t parity)
+{
+    MBar* b = (MBar*)bar;
+    return (uint32_t)b->phase != (parity & 1);
 }
 inline void bulk_g2s(void* d, const void* s, uint32_t bytes, unsigned long long* bar)
 {
@@ -199,27 +220,36 @@ inline void fiber_entry()
 inline void run_grid(uint32_t grid, uint32_t block, size_t smem_bytes, const std::function<void()>& body)
 {
     State& s = S();
-    const size_t STACK = 256 * 1024;
-    static unsigned char* smem_buf = nullptr;
-    if (!smem_buf) smem_buf = (unsigned char*)aligned_alloc(1024, 256 * 1024);
+    const size_t STACK = 128 * 1024;
     if (smem_bytes > 232448) { fprintf(stderr, "emu: %zu bytes of dynamic smem exceed 227 KB\n", smem_bytes); abort(); }
-    s.smem = smem_buf;
+    const char* env = getenv("EMU_CTAS");
+    uint32_t resident = env ? (uint32_t)atoi(env) : 1u;
+    if (resident < 1) resident = 1;
+    if (resident > grid) resident = grid;
     s.body = &body;
-    if (s.fibers.size() < block) {
+    if (s.blocks.size() < resident) s.blocks.resize(resident);
+    for (uint32_t k = 0; k < resident; ++k)
+        if (!s.blocks[k].smem) s.blocks[k].smem = (unsigned char*)aligned_alloc(1024, 256 * 1024);
+    if (s.fibers.size() < (size_t)resident * block) {
         size_t old = s.fibers.size();
-        s.fibers.resize(block);
-        for (size_t i = old; i < block; ++i) s.fibers[i].stack = (char*)malloc(STACK);
+        s.fibers.resize((size_t)resident * block);
+        for (size_t i = old; i < s.fibers.size(); ++i) s.fibers[i].stack = (char*)malloc(STACK);
     }
-    uint32_t nw = (block + 31) / 32;
-    for (uint32_t b = 0; b < grid; ++b) {
-        s.bar_count = 0; s.bar_gen = 0;
-        memset(s.nbar_count, 0, sizeof(s.nbar_count)); memset(s.nbar_gen, 0, sizeof(s.nbar_gen));
-        s.wbar_count.assign(nw, 0); s.wbar_gen.assign(nw, 0);
-        s.xch.assign((size_t)nw * 32, 0);
-        memset(smem_buf, 0xA5, smem_bytes);              // uninitialised shared memory is garbage
+    const uint32_t nw = (block + 31) / 32;
+    uint32_t next_block = 0, running = 0;
+    auto start = [&](uint32_t slot, uint32_t b) {
+        Block& B = s.blocks[slot];
+        B.bar_count = 0; B.bar_gen = 0;
+        memset(B.nbar_count, 0, sizeof(B.nbar_count)); memset(B.nbar_gen, 0, sizeof(B.nbar_gen));
+        B.wbar_count.assign(nw, 0); B.wbar_gen.assign(nw, 0);
+        B.xch.assign((size_t)nw * 32, 0);
+        memset(B.smem, 0xA5, smem_bytes);                // uninitialised shared memory is garbage
+        B.alive = block;
+        B.active = true;
         for (uint32_t t = 0; t < block; ++t) {
-            Fiber& f = s.fibers[t];
+            Fiber& f = s.fibers[(size_t)slot * block + t];
             f.done = false;
+            f.slot = (int)slot;
             f.tc = ThreadCtx{t, b, block, grid};
             getcontext(&f.ctx);
             f.ctx.uc_stack.ss_sp = f.stack;
@@ -227,19 +257,29 @@ inline void run_grid(uint32_t grid, uint32_t block, size_t smem_bytes, const std
             f.ctx.uc_link = nullptr;
             makecontext(&f.ctx, (void (*)())fiber_entry, 0);
         }
-        uint32_t alive = block;
-        s.yields_without_progress = 0;
-        while (alive) {
+    };
+    for (uint32_t k = 0; k < resident; ++k) { s.blocks[k].active = false; }
+    for (uint32_t k = 0; k < resident && next_block < grid; ++k) { start(k, next_block++); ++running; }
+    s.yields_without_progress = 0;
+    while (running) {
+        for (uint32_t k = 0; k < resident; ++k) {
+            Block& B = s.blocks[k];
+            if (!B.active) continue;
             for (uint32_t t = 0; t < block; ++t) {
-                Fiber& f = s.fibers[t];
+                Fiber& f = s.fibers[(size_t)k * block + t];
                 if (f.done) continue;
-                s.current = (int)t;
+                s.current = (int)((size_t)k * block + t);
                 swapcontext(&s.sched, &f.ctx);
-                if (f.done) --alive;
+                if (f.done) --B.alive;
+            }
+            if (B.alive == 0) {                          // the CTA has retired: the next one of the grid takes its place
+                B.active = false;
+                --running;
+                if (next_block < grid) { start(k, next_block++); ++running; }
             }
         }
-        s.current = -1;
     }
+    s.current = -1;
 }
 
 // minimal runtime shims used by the launch sequences in codec_launch.cuh

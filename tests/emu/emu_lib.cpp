@@ -19,7 +19,7 @@ int emu_encode(const void* px, int dtype, size_t n, size_t frames, unsigned bloc
     if (used_fast) *used_fast = pl.fast ? 1 : 0;
     void* scratch = malloc(pl.scratch_bytes);
     memset(scratch, 0x5A, pl.scratch_bytes);
-    Launcher L{nullptr, 1, nullptr, cudaSuccess};
+    Launcher L{nullptr, getenv("EMU_SMS") ? (u32)atoi(getenv("EMU_SMS")) : 1u, nullptr, cudaSuccess};
     encode_async(L, dtype, px, n, frames, block, out, cap, (u64*)frame_ends, prolix_bits, status, scratch, pl,
                  3, dbg_incl_stride);
     free(scratch);

@@ -6,9 +6,9 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "emu", "emu_lib.cpp")
 OUT = os.path.join(ROOT, "tests", "emu", "libtrpx_emu.so")
-DEPS = [SRC, os.path.join(ROOT, "tests", "emu", "emu.hpp")] + [
-    os.path.join(ROOT, "trpx_b200", "csrc", f) for f in
-    ("simt.cuh", "terse_encode.cuh", "prolix_decode.cuh", "codec_launch.cuh")]
+CSRC = os.path.join(ROOT, "trpx_b200", "csrc")
+DEPS = [SRC, os.path.join(ROOT, "tests", "emu", "emu.hpp")] + sorted(
+    os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh"))
 
 
 def build(force=False):

@@ -28,8 +28,16 @@ def _aligned(nbytes, align=16, offset=0):
     return raw[start:start + nbytes]
 
 
-def encode(stack, block=12, incl_stride=0, misalign=0, cap=None):
+def _set_grid(ctas, sms):
+    """ctas: CTAs of a grid that are resident (interleaved) at once; sms: the emulated device's SM count (grid size)."""
+    import os
+    os.environ["EMU_CTAS"] = str(ctas)
+    os.environ["EMU_SMS"] = str(sms)
+
+
+def encode(stack, block=12, incl_stride=0, misalign=0, cap=None, ctas=1, sms=1):
     """stack: (F, N) array.  Returns (payload, frame_ends, prolix_bits, status, used_fast)."""
+    _set_grid(ctas, sms)
     stack = np.ascontiguousarray(stack)
     F, N = stack.shape
     dt = orc.code_of(stack.dtype)

@@ -48,7 +48,7 @@ def lib(build_if_missing=True):
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.OUT
+    path = os.environ.get("TRPX_LIB") or _build.OUT      # TRPX_LIB: an A/B variant built by tools/build_variant.py
     if not os.path.exists(path):
         if not build_if_missing:
             raise TrpxError(ERR_NO_DEVICE, "libtrpx_b200.so has not been built")

@@ -673,7 +673,10 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_resolve_kernel(DecParams p)
         grid_sync();
         const u32 any = ld_relaxed(flag);
         if (!any) break;
-        if (sweep > (1u << 22)) trap();
+        if (sweep > (1u << 16)) {                           // (every CTA counts the same sweeps: all of them leave here together)
+            if (gtid == 0) atomic_max(p.status, DEC_MALFORMED);
+            break;
+        }
     }
     // descriptors of table entries past the last segment say "nothing here" (the unpack grid covers max_segs)
     if (p.segd)

@@ -193,15 +193,57 @@ TRPX_DEVICE bool mbar_try_wait(u64* bar, u32 parity)
         : "memory");
     return ok != 0;
 }
-TRPX_DEVICE void mbar_wait(u64* bar, u32 parity)
+TRPX_DEVICE bool mbar_test(u64* bar, u32 parity) { return mbar_try_wait(bar, parity); }   // non-blocking: has that phase completed?
+// 32 x 32 -> 64-bit product on the FMA pipe (IMAD.WIDE).  The bit packers shift by multiplying with a power of two:
+// the ALU pipe (LOP3 / SHF / IADD3 / SEL / ISETP, half rate) is what bounds them, the FMA pipe is idle.  Inline PTX,
+// because the compiler would turn a multiplication by (1 << n) back into shifts.
+TRPX_DEVICE u64 mul_wide(u32 a, u32 b)
 {
-    // bounded: a mis-programmed barrier must trap, never hang the box
-    for (u32 spins = 0; !mbar_try_wait(bar, parity); ++spins)
-        if (spins > (1u << 26)) trap();
+    u64 r;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b));
+    return r;
 }
-
-// For long, uncritical waits (the resolver warps are idle most of the time): let the hardware suspend
-// the thread inside try_wait for up to `hint` ns instead of burning issue slots in a spin loop.
+TRPX_DEVICE u32 mul_lo(u32 a, u32 b)           // a * b (IMAD), opaque to the strength reducer for the same reason
+{
+    u32 r;
+    asm("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+TRPX_DEVICE u32 mad_lo(u32 a, u32 b, u32 c)    // a * b + c (IMAD)
+{
+    u32 r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+// Every wait in the kernels is bounded and NEVER traps (a trap poisons the CUDA context of the whole process): a
+// wait that runs out raises an internal status word (>= ST_INTERNAL, the code names the wait) and gives up; every
+// other wait sees that word and gives up too, so the kernel ends and the host reports TRPX_ERR_CUDA for the call.
+constexpr u32 ST_INTERNAL = 0x100;
+TRPX_DEVICE u64 now_ns()
+{
+    u64 t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// limit_log2: the wait may last 2^limit_log2 microseconds (measured with %globaltimer every 256 polls)
+struct WaitClock {
+    u64 t0 = 0;
+    TRPX_DEVICE bool expired(u32* status, u32 spins, u32 limit_log2, u32 code)
+    {
+        if ((spins & 255u) != 255u) return false;
+        const u64 t = now_ns();
+        if (!t0) t0 = t;
+        if ((t - t0) >> (limit_log2 + 10)) {                 // the FIRST wait that runs out names the failure
+            u32 old = *(volatile u32*)status;
+            while (old < ST_INTERNAL) {
+                const u32 prev = atomicCAS(status, old, ST_INTERNAL + code);
+                if (prev == old) break;
+                old = prev;
+            }
+        }
+        return *(volatile u32*)status >= ST_INTERNAL;
+    }
+};
 TRPX_DEVICE bool mbar_try_wait_hint(u64* bar, u32 parity, u32 hint_ns)
 {
     u32 ok;
@@ -214,10 +256,17 @@ TRPX_DEVICE bool mbar_try_wait_hint(u64* bar, u32 parity, u32 hint_ns)
         : "memory");
     return ok != 0;
 }
-TRPX_DEVICE void mbar_wait_sleep(u64* bar, u32 parity)
+TRPX_DEVICE void mbar_wait(u64* bar, u32 parity, u32* status, u32 code)
 {
-    for (u32 spins = 0; !mbar_try_wait_hint(bar, parity, 200000u); ++spins)
-        if (spins > (1u << 24)) trap();
+    WaitClock wc;
+    for (u32 spins = 0; !mbar_try_wait_hint(bar, parity, 1000u); ++spins)
+        if (wc.expired(status, spins, 21, code)) break;
+}
+TRPX_DEVICE void mbar_wait_sleep(u64* bar, u32 parity, u32* status, u32 code)
+{
+    WaitClock wc;
+    for (u32 spins = 0; !mbar_try_wait_hint(bar, parity, 20000u); ++spins)
+        if (wc.expired(status, spins, 23, code)) break;
 }
 
 // ---- TMA bulk copies (1-D): SASS UBLKCP ----
@@ -376,8 +425,23 @@ inline void mbar_init(u64* bar, u32 count) { ::emu::mbar_init(bar, count); }
 inline void mbar_init_fence() {}
 inline void mbar_arrive_expect_tx(u64* bar, u32 bytes) { ::emu::mbar_arrive_expect_tx(bar, bytes); }
 inline void mbar_arrive(u64* bar) { ::emu::mbar_arrive(bar); }
-inline void mbar_wait(u64* bar, u32 parity) { ::emu::mbar_wait(bar, parity); }
-inline void mbar_wait_sleep(u64* bar, u32 parity) { ::emu::mbar_wait(bar, parity); }
+constexpr u32 ST_INTERNAL = 0x100;
+struct WaitClock {
+    bool expired(u32* status, u32 spins, u32 limit_log2, u32 code)
+    {
+        if (spins == (1u << 16)) fprintf(stderr, "emu: long wait: bid %u tid %u code %u (warp %u, round %u)\n", ::emu::cur().bid, ::emu::cur().tid, code & 15, (code >> 4) & 31, code >> 12);
+        if (spins >> 18) { fprintf(stderr, "emu: wait %u (code %u, warp %u, round %u) expired\n", code, code & 15, (code >> 4) & 31, code >> 12); ::emu::trap(); }
+        (void)limit_log2;
+        (void)status;
+        return false;
+    }
+};
+inline void mbar_wait(u64* bar, u32 parity, u32*, u32 code) { ::emu::mbar_wait(bar, parity, code); }
+inline bool mbar_test(u64* bar, u32 parity) { return ::emu::mbar_test(bar, parity); }
+inline u64 mul_wide(u32 a, u32 b) { return (u64)a * b; }
+inline u32 mul_lo(u32 a, u32 b) { return a * b; }
+inline u32 mad_lo(u32 a, u32 b, u32 c) { return a * b + c; }
+inline void mbar_wait_sleep(u64* bar, u32 parity, u32*, u32 code) { ::emu::mbar_wait(bar, parity, code); }
 inline void bulk_g2s(void* d, const void* s, u32 bytes, u64* bar) { ::emu::bulk_g2s(d, s, bytes, bar); }
 inline void bulk_s2g(void* d, const void* s, u32 bytes) { ::emu::bulk_s2g(d, s, bytes); }
 inline void bulk_commit() {}

@@ -222,7 +222,12 @@ __global__ void publish_results_kernel(const u64* d_ends, u64 n, const u32* d_sm
     if (blockIdx.x == 0 && threadIdx.x < 2) h_small[threadIdx.x] = d_small[threadIdx.x];
 }
 
-int status_of_device_word(u32 w) { return w == 0 ? TRPX_OK : (int)w; }
+// device status words: 0, a TRPX_ERR_* code, or >= ST_INTERNAL when a bounded wait inside a kernel ran out (simt.cuh)
+int status_of_device_word(u32 w) { return w == 0 ? TRPX_OK : w >= ST_INTERNAL ? TRPX_ERR_CUDA : (int)w; }
+void note_device_word(trpx_ctx* c, u32 w)
+{
+    if (w >= ST_INTERNAL && c) c->last_error = "a bounded wait inside a kernel ran out (internal code " + std::to_string(w - ST_INTERNAL) + ")";
+}
 
 }  // namespace
 
@@ -469,7 +474,7 @@ int trpx_encode_host(trpx_ctx* c, const void* pixels, int dtype, size_t n_values
         if (!q.active) return TRPX_OK;
         q.active = false;
         if (!cuda_ok(c, cudaStreamSynchronize(l.stream), "encode batch")) return TRPX_ERR_CUDA;
-        if (l.h_small[1] != 0) return status_of_device_word(l.h_small[1]);
+        if (l.h_small[1] != 0) { note_device_word(c, l.h_small[1]); return status_of_device_word(l.h_small[1]); }
         const size_t bytes = (size_t)l.h_ends[q.nf - 1];
         if (out_off + bytes > out_capacity) return TRPX_ERR_CAPACITY;
         if (!cuda_ok(c, cudaMemcpyAsync(out + out_off, l.d_out.p, bytes, cudaMemcpyDeviceToHost, l.copy_stream), "D2H payload") ||
@@ -657,7 +662,7 @@ int trpx_decode_host(trpx_ctx* c, const uint8_t* payload, size_t payload_bytes, 
         if (!cuda_ok(c, cudaMemcpy(c->call_status.data(), c->d_call_status.p, issued * sizeof(u32), cudaMemcpyDeviceToHost), "D2H status"))
             return TRPX_ERR_CUDA;
         for (size_t b = 0; b < issued; ++b)
-            if (c->call_status[b] != 0) return status_of_device_word(c->call_status[b]);
+            if (c->call_status[b] != 0) { note_device_word(c, c->call_status[b]); return status_of_device_word(c->call_status[b]); }
     }
     return rc;
 }
