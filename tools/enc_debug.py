@@ -27,6 +27,12 @@ def run(F, check=4):
         want, per, pb = orc.encode_stack(host)
         got = payload[:int(e[check - 1])].cpu().numpy()
         ok = np.array_equal(got, want) and np.array_equal(e[:check], np.cumsum(per).astype(np.int64))
+    if os.environ.get("TRPX_STATS"):
+        capb = cap & ~15
+        dbg = payload[capb - 256:capb - 96].cpu().numpy().view(np.uint64)
+        names = ["wait_full", "wait_ticket", "forced_drain", "early_drain", "final_drain", "n_forced", "n_early", "rounds", "total", "pack", "n_tail_fetch", "drain_wait_resolved", "L:load", "L:ticket+issue", "L:K1-K3", "L:post+alloc", "L:pack", "L:merge", "L:publish", "L:early"]
+        tot = float(dbg[8]) or 1.0
+        print("  stats (cycles summed over worker warps; %% of total): " + ", ".join("%s=%.3g (%.1f%%)" % (n, float(v), 100 * float(v) / tot) for n, v in zip(names, dbg) if n != "-"))
     print("F=%d status=0x%x (code %d warp %d round %d) bytes=%d first-frames-ok=%s pb=%d" % (F, status, status & 15, (status >> 4) & 31, status >> 12, int(e[-1]), ok, int(small[0])), flush=True)
     codec.close()
 

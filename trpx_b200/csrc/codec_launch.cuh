@@ -7,7 +7,6 @@
 
 #include "simt.cuh"
 #include "terse_encode.cuh"
-#include "terse_warp.cuh"
 #include "prolix_decode.cuh"
 
 namespace trpx {
@@ -61,7 +60,6 @@ struct EncPlan {
     bool fast;                  // block == 12 and 16-byte aligned frames: TMA-staged kernel
     u32 tile_blocks;
     u64 nblocks, tiles_per_frame, n_tiles, groups_per_frame, n_groups;
-    u64 n_wtiles;               // boundary-word hand-off slots: warp tiles (fast path) or tiles
     u32 threads;                // threads per CTA
     size_t smem;                // dynamic shared memory per CTA
     size_t scratch_bytes;       // ticket + tile descriptors + tails + group descriptors
@@ -75,10 +73,10 @@ inline EncPlan enc_plan_t(const void* d_pixels, u64 n_values, u64 n_frames, u32 
     pl.ok = true;
     pl.nblocks = div_up(n_values, block);
     pl.fast = block == 12 && ((uintptr_t)d_pixels & 15) == 0 && ((n_values * sizeof(T)) & 15) == 0;
-    if (pl.fast) {                                       // a "tile" of the look-back is a supertile: ENC_NW warp tiles
-        pl.tile_blocks = WGeom<T, ENC_NW>::ST_BLOCKS;
-        pl.smem = WGeom<T, ENC_NW>::SMEM_BYTES;
-        pl.threads = WGeom<T, ENC_NW>::THREADS;
+    if (pl.fast) {
+        pl.tile_blocks = EncGeom<T, EncNT<T>::V>::TILE_BLOCKS;
+        pl.smem = EncGeom<T, EncNT<T>::V>::SMEM_BYTES;
+        pl.threads = EncGeom<T, EncNT<T>::V>::THREADS;
     } else {
         pl.threads = GEN_NT;
         const u64 maxbits = 12 + (u64)block * (Pix<T>::W + (Pix<T>::SGN ? 1 : 0));
@@ -94,8 +92,7 @@ inline EncPlan enc_plan_t(const void* d_pixels, u64 n_values, u64 n_frames, u32 
     if (pl.n_tiles >= (1ull << 31)) pl.ok = false;
     pl.groups_per_frame = div_up(pl.tiles_per_frame, GROUP);
     pl.n_groups = pl.groups_per_frame * n_frames;
-    pl.n_wtiles = pl.fast ? pl.n_tiles * ENC_NW : pl.n_tiles;
-    pl.scratch_bytes = 64 + (size_t)pl.n_tiles * 8 + (size_t)pl.n_wtiles * 8 + (size_t)pl.n_groups * 8;
+    pl.scratch_bytes = 64 + (size_t)pl.n_tiles * 16 + (size_t)pl.n_groups * 8;
     return pl;
 }
 
@@ -120,7 +117,7 @@ inline void encode_launch_t(Launcher& L, const EncPlan& pl, EncParams p, u32 cta
     if (grid > pl.n_tiles) grid = pl.n_tiles;
     if (grid == 0) return;
     if (pl.fast)
-        L.err = launch(terse_encode_warp_kernel<T, ENC_NW>, (u32)grid, pl.threads, pl.smem, L.stream, p);
+        L.err = launch(terse_encode_kernel<T, EncNT<T>::V>, (u32)grid, pl.threads, pl.smem, L.stream, p);
     else
         L.err = launch(terse_encode_generic_kernel<T, GEN_NT>, (u32)grid, GEN_NT, pl.smem, L.stream, p,
                        pl.tile_blocks);
@@ -130,7 +127,7 @@ inline void encode_launch_t(Launcher& L, const EncPlan& pl, EncParams p, u32 cta
 template <typename T>
 inline const void* enc_kernel_t(bool fast)
 {
-    return fast ? (const void*)terse_encode_warp_kernel<T, ENC_NW> : (const void*)terse_encode_generic_kernel<T, GEN_NT>;
+    return fast ? (const void*)terse_encode_kernel<T, EncNT<T>::V> : (const void*)terse_encode_generic_kernel<T, GEN_NT>;
 }
 inline const void* enc_kernel(int dtype, bool fast)
 {
@@ -169,7 +166,7 @@ inline void encode_async(Launcher& L, int dtype, const void* d_pixels, u64 n_val
     p.ticket = (u32*)scratch;
     p.tdesc = (u64*)((unsigned char*)scratch + 64);
     p.tails = p.tdesc + pl.n_tiles;
-    p.gdesc = p.tails + pl.n_wtiles;
+    p.gdesc = p.tails + pl.n_tiles;
     p.dbg_incl_stride = dbg_incl_stride & 0xffffu;
     p.dbg_ring_words = dbg_incl_stride >> 16;
     cudaMemsetAsync(scratch, 0, pl.scratch_bytes, L.stream);

@@ -29,6 +29,8 @@ typedef unsigned int u32;
 #ifndef TRPX_EMU
 // ----------------------------------------------------------------------------- CUDA backend
 #define TRPX_DEVICE __device__ __forceinline__
+#define TRPX_DEVICE_NOINLINE __device__ __noinline__
+#define TRPX_GRID_CONSTANT __grid_constant__
 #define TRPX_HD __host__ __device__ __forceinline__
 #define TRPX_KERNEL __global__
 #define TRPX_SHARED __shared__
@@ -181,6 +183,10 @@ TRPX_DEVICE void mbar_arrive(u64* bar)    // release.cta: the arriving thread's 
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
+TRPX_DEVICE void mbar_arrive_relaxed(u64* bar)   // no ordering of the thread's other memory operations
+{
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
 TRPX_DEVICE bool mbar_try_wait(u64* bar, u32 parity)
 {
     u32 ok;
@@ -258,15 +264,20 @@ TRPX_DEVICE bool mbar_try_wait_hint(u64* bar, u32 parity, u32 hint_ns)
 }
 TRPX_DEVICE void mbar_wait(u64* bar, u32 parity, u32* status, u32 code)
 {
+    if (mbar_try_wait(bar, parity)) return;
     WaitClock wc;
-    for (u32 spins = 0; !mbar_try_wait_hint(bar, parity, 1000u); ++spins)
+    for (u32 spins = 0; !mbar_try_wait_hint(bar, parity, 1000u); ++spins) {   // (the hint alone does not stop the polling)
         if (wc.expired(status, spins, 21, code)) break;
+        __nanosleep(100);
+    }
 }
 TRPX_DEVICE void mbar_wait_sleep(u64* bar, u32 parity, u32* status, u32 code)
 {
     WaitClock wc;
-    for (u32 spins = 0; !mbar_try_wait_hint(bar, parity, 20000u); ++spins)
+    for (u32 spins = 0; !mbar_try_wait_hint(bar, parity, 20000u); ++spins) {
         if (wc.expired(status, spins, 23, code)) break;
+        __nanosleep(400);
+    }
 }
 
 // ---- TMA bulk copies (1-D): SASS UBLKCP ----
@@ -317,6 +328,8 @@ inline cudaError_t launch_coop(void (*kern)(P), u32 grid, u32 block, size_t smem
 #else
 // ----------------------------------------------------------------------------- emulation backend
 #define TRPX_DEVICE inline
+#define TRPX_DEVICE_NOINLINE inline
+#define TRPX_GRID_CONSTANT
 #define TRPX_HD inline
 #define TRPX_KERNEL
 #define TRPX_SHARED static
@@ -425,6 +438,7 @@ inline void mbar_init(u64* bar, u32 count) { ::emu::mbar_init(bar, count); }
 inline void mbar_init_fence() {}
 inline void mbar_arrive_expect_tx(u64* bar, u32 bytes) { ::emu::mbar_arrive_expect_tx(bar, bytes); }
 inline void mbar_arrive(u64* bar) { ::emu::mbar_arrive(bar); }
+inline void mbar_arrive_relaxed(u64* bar) { ::emu::mbar_arrive(bar); }
 constexpr u32 ST_INTERNAL = 0x100;
 struct WaitClock {
     bool expired(u32* status, u32 spins, u32 limit_log2, u32 code)

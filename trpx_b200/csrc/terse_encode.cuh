@@ -30,6 +30,9 @@
 #ifndef ENC_UNIT_U32
 #define ENC_UNIT_U32 96
 #endif
+#ifndef ENC_UNIT_U16
+#define ENC_UNIT_U16 96
+#endif
 
 namespace trpx {
 
@@ -88,7 +91,7 @@ struct Pix {
     static constexpr int SZ = (int)sizeof(T);
     static constexpr int W = 8 * SZ;
     static constexpr bool SGN = T(-1) < T(0);
-    static constexpr int UNIT_BYTES = SZ == 8 ? 96 : SZ == 2 ? 96 : SZ == 1 ? ENC_UNIT_U8 : ENC_UNIT_U32;    // bytes one thread owns (3 or 6 LDS.128)
+    static constexpr int UNIT_BYTES = SZ == 8 ? 96 : SZ == 2 ? ENC_UNIT_U16 : SZ == 1 ? ENC_UNIT_U8 : ENC_UNIT_U32;    // bytes one thread owns (3 or 6 LDS.128)
     static constexpr int UW = UNIT_BYTES / 4;               // 32-bit words per unit
     static constexpr int VPU = UNIT_BYTES / SZ;             // values per unit: 48 / 24 / 12 / 12
     static constexpr int BPU = VPU / 12;                    // blocks per unit:  4 /  2 /  1 /  1
@@ -229,6 +232,16 @@ struct BitSink {
 // value i of a block held in words, as a sign-extended 64-bit pattern
 template <typename T>
 TRPX_DEVICE u64 block_value(const u32* w, int i)
+{
+    typedef Pix<T> P;
+    if (P::SZ == 1) { u32 b = (w[i >> 2] >> (8 * (i & 3))) & 0xffu; return P::SGN ? (u64)(i64)(int8_t)b : b; }
+    if (P::SZ == 2) { u32 h = (w[i >> 1] >> (16 * (i & 1))) & 0xffffu; return P::SGN ? (u64)(i64)(int16_t)h : h; }
+    if (P::SZ == 4) return P::SGN ? (u64)(i64)(int)w[i] : (u64)w[i];
+    return (u64)w[2 * i] | ((u64)w[2 * i + 1] << 32);
+}
+
+template <typename T>
+TRPX_DEVICE u64 block_value_dyn(const u32* w, u32 i)       // the same, for an index only known at run time (w in memory)
 {
     typedef Pix<T> P;
     if (P::SZ == 1) { u32 b = (w[i >> 2] >> (8 * (i & 3))) & 0xffu; return P::SGN ? (u64)(i64)(int8_t)b : b; }
@@ -530,12 +543,289 @@ TRPX_DEVICE void resolve_and_store(const EncParams& p, u64 tile, u32 tile_bits, 
 }
 
 // ------------------------------------------------------------------ shared-memory layout
-constexpr int SM_TICKETS = 192;     // u32 ticket of the tile in progress
+constexpr int ENC_STAGES = 2;       // TMA pixel stages
+constexpr int ENC_DEPTH = 6;        // tiles a CTA may have packed but not yet stored (mailbox entries)
+constexpr int ENC_RESOLVERS = 2;    // resolver warps; resolver r serves iterations it % ENC_RESOLVERS == r
+static_assert(ENC_DEPTH % ENC_RESOLVERS == 0, "a mailbox entry is always served by the same resolver");
+static_assert(2 + 2 * ENC_DEPTH <= 16, "named barriers: 0 CTA, 1 workers, 2.. ready, 2+DEPTH.. packed");
+constexpr int SM_BARS = 0;          // mbarriers, 8 bytes each: full[STAGES], ready[DEPTH], packed[DEPTH], resolved[DEPTH]
+constexpr int SM_TICKETS = 192;     // 2 x ENC_STAGES u32: tile, tile-in-frame
 constexpr int SM_WARP_TOT = 256;    // 32 u32
 constexpr int SM_WARP_LAST = 384;   // 32 u32
 constexpr int SM_BCAST = 512;       // 4 u64 (generic kernel)
 constexpr int SM_MAX = 544;         // u32 running max width
+constexpr int SM_MAIL = 576;        // ENC_DEPTH x {u64 tile, u64 P0, u32 bits, u32 tail_in, u32 tail_out, u32 ring word} (32 bytes each)
 constexpr int SM_HEADER = 1024;
+static_assert(8 * (ENC_STAGES + 3 * ENC_DEPTH) <= SM_TICKETS && SM_MAIL + 40 * ENC_DEPTH <= SM_HEADER, "shared-memory header layout");
+constexpr u64 TILE_END = ~0ull;
+
+template <typename T, int NT>
+struct EncGeom {
+    typedef Pix<T> P;
+    static constexpr int TILE_BYTES = NT * P::UNIT_BYTES;
+    static constexpr int TILE_BLOCKS = NT * P::BPU;
+    static constexpr int STAGE_BYTES = ((P::UNIT_BYTES + TILE_BYTES + 127) / 128) * 128;   // halo + tile
+    // Packed tiles wait in a ring of words until their stream position is known.  A tile takes
+    // (bits / 32 + 1) words plus a zero word on either side (window_word), rounded to 4: ~0.7 K words
+    // for a typical 512^2 u16 tile, WORST_WORDS when nothing compresses.  The ring always holds two
+    // worst-case tiles; with typical data ENC_DEPTH tiles are in flight.
+    static constexpr int WORST_WORDS = ((TILE_BLOCKS * P::MAXBITS + 31) / 32 + 1 + 3 + 3) / 4 * 4;
+    static constexpr int RING_WORDS = (2 * WORST_WORDS <= 8192 || (P::SZ <= 4 && WORST_WORDS <= 8192)) ? 8192 : (2 * WORST_WORDS <= 16384 ? 16384 : 32768);   // a power of two
+    static constexpr int SMEM_BYTES = SM_HEADER + ENC_STAGES * STAGE_BYTES + RING_WORDS * 4;
+    static constexpr int THREADS = NT + 32 * ENC_RESOLVERS;   // worker warps + resolver warps
+};
+
+// ------------------------------------------------------------------ fast kernel: block == 12, 16-byte aligned frames
+// Warp-specialised persistent CTA.
+//   workers (NT threads)   wait for a TMA-staged tile, keep their 48 bytes in registers, compute widths /
+//                          headers / lengths, scan, publish the tile's bit count, and pack the tile into
+//                          the staging ring in tile-relative coordinates.  Packed tiles are stored --
+//                          shifted into place, coalesced streaming stores -- up to ENC_DEPTH iterations
+//                          later, by which time their stream position has long been resolved: workers
+//                          never wait for a global-memory round trip.  Their blocking points are the TMA
+//                          full-barrier (prefetched two tiles ahead) and a resolution that is really late.
+//   resolvers (ENC_RESOLVERS warps, alternating tiles)
+//                          find the tile's stream position with the two-level look-back and exchange the
+//                          boundary word with the neighbour tile: pure latency, off the workers' path.
+template <typename T, int NT>
+TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT + 32 * ENC_RESOLVERS, (EncGeom<T, NT>::SMEM_BYTES > 75 * 1024 ? 2 : 3)) terse_encode_kernel(EncParams p)
+{
+    typedef Pix<T> P;
+    typedef EncGeom<T, NT> G;
+    TRPX_DYN_SMEM(sm);
+    u64* bars = (u64*)(sm + SM_BARS);
+    u64* bar_full = bars;
+    u64* bar_resolved = bars + ENC_STAGES;              // (ready / packed are named barriers 2.. and 2+DEPTH..)
+    u32* tickets = (u32*)(sm + SM_TICKETS);
+    u32* vbases = (u32*)(sm + SM_TICKETS + 32);                         // [ENC_DEPTH] virtual ring offset of a pending tile
+    volatile u64* pn64 = (volatile u64*)(sm + SM_MAIL + 32 * ENC_DEPTH);  // [ENC_DEPTH] end position of a resolved tile
+    u32* sm_warp_tot = (u32*)(sm + SM_WARP_TOT);
+    u32* sm_warp_last = (u32*)(sm + SM_WARP_LAST);
+    u32* sm_max = (u32*)(sm + SM_MAX);
+    volatile u64* mail64 = (volatile u64*)(sm + SM_MAIL);               // [e * 4 + {0: tile, 1: P0}]
+    volatile u32* mail32 = (volatile u32*)(sm + SM_MAIL);               // [e * 8 + {4: bits, 5: tail_in, 6: tail_out, 7: ring word}]
+    unsigned char* stages = sm + SM_HEADER;
+    u32* ring = (u32*)(stages + ENC_STAGES * G::STAGE_BYTES);
+
+    const u32 t = tid(), lane = t & 31, warp = t >> 5;
+    const u64 frame_bytes = p.n_values * P::SZ;
+
+    if (t == 0) {
+        for (int s = 0; s < ENC_STAGES; ++s) mbar_init(&bar_full[s], 1);
+        for (int e = 0; e < ENC_DEPTH; ++e) {
+            mbar_init(&bar_resolved[e], 1);
+        }
+        mbar_init_fence();
+        *sm_max = 0;
+    }
+    sync_block();
+
+    if (t >= (u32)NT) {
+        // ================================================================ resolver warp r
+        for (u32 it = (t - NT) >> 5;; it += ENC_RESOLVERS) {
+            const u32 e = it % ENC_DEPTH, use = it / ENC_DEPTH;
+            bar_sync(2 + e, 64);                           // blocks in hardware until worker warp 0 has posted the tile (no spin)
+            const u64 tile = mail64[e * 4];
+            const u32 tile_bits = mail32[e * 8 + 4];
+            if (tile == TILE_END) break;
+            const u32* stg = ring + mail32[e * 8 + 7];
+            const TileGeom g = tile_geom(p, tile);
+            const u64 P0 = tile_start(p, tile, g, tile_bits, false);
+            const u64 Pn = g.ends ? align_frame(P0 + tile_bits) : P0 + tile_bits;
+            bar_sync(2 + ENC_DEPTH + e, NT + 32);          // all workers have packed: their staging stores are visible now
+            if (lane == 0) {
+                u32 tout;
+                const u32 tin = tail_handoff(p, tile, stg, tile_bits, P0, Pn, tout);
+                mail64[e * 4 + 1] = P0;
+                mail32[e * 8 + 5] = tin;
+                mail32[e * 8 + 6] = tout;
+                pn64[e] = Pn;
+                mbar_arrive(&bar_resolved[e]);
+            }
+            sync_warp();
+        }
+        return;
+    }
+
+    // ==================================================================== worker warps
+    // thread 0 is also the TMA producer: take the next ticket, start that tile's bulk copy
+    auto issue = [&](int s) {
+        const u32 tk = atomic_add(p.ticket, 1u);
+        tickets[s] = tk;
+        if ((u64)tk < p.n_tiles) {
+            const u32 tpf = (u32)p.tiles_per_frame;
+            const u64 f = tk / tpf, tif = tk - (u32)f * tpf;
+            tickets[ENC_STAGES + s] = (u32)tif;
+            const u64 tile_off = tif * (u64)G::TILE_BYTES;
+            u64 bytes = frame_bytes - tile_off;
+            if (bytes > (u64)G::TILE_BYTES) bytes = G::TILE_BYTES;
+            const unsigned char* src = (const unsigned char*)p.pixels + f * frame_bytes + tile_off;
+            unsigned char* dst = stages + s * G::STAGE_BYTES + P::UNIT_BYTES;
+            if (tif > 0) { src -= P::UNIT_BYTES; dst -= P::UNIT_BYTES; bytes += P::UNIT_BYTES; }   // halo: previous block
+            mbar_arrive_expect_tx(&bar_full[s], (u32)bytes);
+            bulk_g2s(dst, src, (u32)bytes, &bar_full[s]);
+        }
+    };
+    // store the tile packed in iteration `j`, once resolved
+    auto store_pending = [&](u32 j) {
+        const u32 e = j % ENC_DEPTH;
+        mbar_wait(&bar_resolved[e], (j / ENC_DEPTH) & 1, p.status, 6);
+        const u64 ptile = mail64[e * 4];
+        const u64 P0 = mail64[e * 4 + 1], Pn = pn64[e];
+        const u32 pbits = mail32[e * 8 + 4];
+        TileGeom g;
+        if (t == 0) g = tile_geom(p, ptile);               // only rank 0 needs the frame bookkeeping
+        else { g.frame = 0; g.ends = false; }
+        store_tile(p, ptile, g, ring + mail32[e * 8 + 7], pbits, P0, Pn, mail32[e * 8 + 5], mail32[e * 8 + 6], t, NT);
+    };
+    if (t == 0)
+        for (int s = 0; s < ENC_STAGES; ++s) issue(s);
+    bar_sync(1, NT);
+
+    // ring bookkeeping, identical in every worker thread: virtual word offsets that only grow; the
+    // tiles of iterations [oldest, it) are packed but not stored and occupy [vtail, vhead)
+    u32 vhead = 0, vtail = 0, oldest = 0;
+    const u32 ring_words = p.dbg_ring_words ? p.dbg_ring_words : (u32)G::RING_WORDS;   // a power of two (tests vary it)
+    const u32 ring_mask = ring_words - 1;
+    u32 my_max = 0;
+    u32 it = 0;
+    for (;; ++it) {
+        const int s = (int)(it % ENC_STAGES);
+        const u32 e = it % ENC_DEPTH;
+        const u64 tile = tickets[s];
+        if (tile >= p.n_tiles) break;
+        const u64 tif = tickets[ENC_STAGES + s];
+
+        mbar_wait(&bar_full[s], (it / ENC_STAGES) & 1, p.status, 7);
+
+        // ---- this thread's unit -> registers
+        u32 w[P::UW];
+        const unsigned char* tile_sm = stages + s * G::STAGE_BYTES + P::UNIT_BYTES;
+        {
+            const uint4* src = (const uint4*)(tile_sm + (size_t)t * P::UNIT_BYTES);
+#pragma unroll
+            for (int j = 0; j < P::UW / 4; ++j) {
+                uint4 v = src[j];
+                w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
+            }
+        }
+        u32 nvalid = P::VPU;
+        if (tif + 1 == p.tiles_per_frame) {                // the frame's last tile may be ragged
+            const u64 tile_vals = p.n_values - tif * (u64)(G::TILE_BLOCKS * 12);
+            const u64 my_first = (u64)t * P::VPU;
+            nvalid = my_first >= tile_vals ? 0u : (tile_vals - my_first > (u64)P::VPU ? (u32)P::VPU : (u32)(tile_vals - my_first));
+            if (nvalid < (u32)P::VPU) {                    // frame tail: wipe what is not ours
+                const u32 vbytes = nvalid * P::SZ;
+#pragma unroll
+                for (int j = 0; j < P::UW; ++j) {
+                    const u32 lo = 4u * j;
+                    if (vbytes <= lo) w[j] = 0;
+                    else if (vbytes < lo + 4) w[j] &= (1u << (8 * (vbytes - lo))) - 1;
+                }
+            }
+        }
+
+        // ---- K1: widths of my blocks
+        u32 sb[P::BPU], cnt[P::BPU];
+#pragma unroll
+        for (int b = 0; b < P::BPU; ++b) {
+            sb[b] = block_width12<T>(&w[b * P::BW]);
+            const u32 v0 = 12u * b;
+            cnt[b] = nvalid <= v0 ? 0u : (nvalid - v0 > 12u ? 12u : nvalid - v0);
+            my_max = sb[b] > my_max ? sb[b] : my_max;
+        }
+        u32 prev0 = 0;                                     // width of the block before the tile
+        if (t == 0 && tif > 0) {
+            u32 h[P::BW];
+            const u32* hs = (const u32*)(tile_sm - 4 * P::BW);
+#pragma unroll
+            for (int j = 0; j < P::BW; ++j) h[j] = hs[j];
+            prev0 = block_width12<T>(h);
+        }
+        if (lane == 31) sm_warp_last[warp] = sb[P::BPU - 1];
+        bar_sync(1, NT);                                   // A: stage `s` is free, warp_last visible
+        if (t == 0) issue(s);
+
+        // ---- K2: headers and lengths
+        u32 prev = shfl_up(sb[P::BPU - 1], 1);
+        if (lane == 0) prev = warp > 0 ? sm_warp_last[warp - 1] : prev0;
+        u32 hv[P::BPU], hl[P::BPU], len = 0;
+#pragma unroll
+        for (int b = 0; b < P::BPU; ++b) {
+            hv[b] = 0; hl[b] = 0;
+            if (cnt[b]) {
+                block_header_fast(sb[b], prev, hv[b], hl[b]);
+                len += hl[b] + sb[b] * cnt[b];
+                prev = sb[b];
+            }
+        }
+
+        // ---- K3: offsets inside the tile
+        u32 off, tile_bits;
+        scan_lengths<NT>(len, sm_warp_tot, off, tile_bits, 1);   // bar B inside
+        // publish the tile's bit count at once: other tiles' look-backs must never wait for our resolver
+        if (t == 0) st_relaxed(&p.tdesc[tile], TD_VALID | (u64)tile_bits);
+
+        // ---- room in the ring: physically contiguous, one zero word in front (window_word reads stg[-1])
+        // words -1 .. (bits/32)+2: a frame end may push the window one word past the zero pad (tail_handoff)
+        const u32 need = ((tile_bits >> 5) + 1 + 3 + 3) & ~3u;
+        u32 vbase = vhead;
+        if ((vbase & ring_mask) + need > ring_words) vbase += ring_words - (vbase & ring_mask);
+        bool stored = false;
+        while (it - oldest == (u32)ENC_DEPTH || (it > oldest && vbase + need - vtail > ring_words)) {
+            store_pending(oldest);                         // blocks only if that resolution is really late
+            ++oldest;
+            vtail = oldest < it ? vbases[oldest % ENC_DEPTH] : vbase;   // virtual base of the next pending tile
+            stored = true;
+        }
+        if (stored) bar_sync(1, NT);                       // E: freed ring words and mailbox entries are reusable
+        u32* stg = ring + (vbase & ring_mask) + 1;
+        if (warp == 0) {
+            if (lane == 0) {
+                mail64[e * 4] = tile;
+                vbases[e] = vbase;
+                mail32[e * 8 + 4] = tile_bits;
+                mail32[e * 8 + 7] = (vbase & ring_mask) + 1;
+                stg[-1] = 0;
+            }
+            sync_warp();
+            bar_arrive(2 + e, 64);                         // the resolver may start its look-back
+        }
+        vhead = vbase + need;
+        if (it == oldest) vtail = vbase;
+        zero_boundary_words<NT>(stg, off, tile_bits);
+        bar_sync(1, NT);                                   // C
+
+        // ---- K4: pack into tile-relative staging
+        BitSink sk;
+        sk.init(stg, off);
+#pragma unroll
+        for (int b = 0; b < P::BPU; ++b)
+            if (cnt[b]) {
+                sk.put(hv[b], hl[b]);
+                pack_block12<T>(sk, &w[b * P::BW], sb[b], cnt[b]);
+            }
+        merge_and_flush(sk, off + len);
+        bar_arrive(2 + ENC_DEPTH + e, NT + 32);            // D: all NT workers arrive -> staging complete
+        // Shared scratch reused by the next iteration is rewritten only after one of its barriers
+        // A..C, which no worker passes before all have finished reading this iteration's values.
+    }
+    // drain: the tiles still waiting in the ring, oldest first
+    for (; oldest < it; ++oldest) store_pending(oldest);
+    bar_sync(1, NT);
+    // tell the resolvers that there is nothing more: the next iteration each of them would serve
+    if (warp == 0) {
+        for (u32 k = 0; k < (u32)ENC_RESOLVERS; ++k) {
+            if (lane == 0) mail64[((it + k) % ENC_DEPTH) * 4] = TILE_END;
+            sync_warp();
+            bar_arrive(2 + (it + k) % ENC_DEPTH, 64);
+        }
+    }
+    my_max = warp_max(my_max);
+    if (lane == 0 && my_max) atomic_max(sm_max, my_max);
+    bar_sync(1, NT);
+    if (t == 0 && *sm_max) atomic_max(p.prolix_bits, *sm_max);
+}
 
 // ------------------------------------------------------------------ generic kernel: any block size / alignment
 // One thread per block, values read straight from global memory (two passes over the block's
