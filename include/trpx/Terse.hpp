@@ -22,6 +22,7 @@
 #include <cassert>
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <istream>
 #include <iterator>
@@ -53,6 +54,66 @@ inline trpx_ctx* context(int device = 0)
     if (h.status != TRPX_OK)
         throw std::runtime_error(std::string("trpx_b200: ") + trpx_strerror(h.status));
     return h.ctx;
+}
+
+// Several GPUs (TRPX_MULTI_GPU=1 in the environment, or jpa::Terse::use_all_devices()): multi-frame calls are sharded
+// by frame over every visible device (trpx_pool_*: one context and one host thread per device, host concatenation).
+inline bool& multi_gpu()
+{
+    static bool on = [] { const char* e = std::getenv("TRPX_MULTI_GPU"); return e && *e && *e != '0'; }();
+    return on;
+}
+inline trpx_pool* pool()
+{
+    struct Holder {
+        trpx_pool* p = nullptr;
+        int status = TRPX_OK;
+        Holder() { status = trpx_pool_create(nullptr, 0, &p); }
+        ~Holder() { trpx_pool_destroy(p); }
+    };
+    static Holder h;
+    if (h.status != TRPX_OK) throw std::runtime_error(std::string("trpx_b200: ") + trpx_strerror(h.status));
+    return h.p;
+}
+
+// Page-locks a caller's range for the duration of one call.  OFF by default: measured on the B200 hosts, registering a
+// 1 GB range costs more than the bounce-buffer copy it saves (bench.py, e2e.dropin: 1.4 k frames/s with, 3.5 k frames/s
+// without).  TRPX_PIN_MIN_MB=<n> turns it on for ranges of at least n MB -- for callers that reuse one buffer for many
+// calls it is cheaper to pin it once themselves (trpx_host_pin).  A range that is pinned already is left alone.
+class ScopedPin {
+public:
+    ScopedPin(const void* p, std::size_t bytes)
+    {
+        static const std::size_t min_bytes = [] {
+            const char* e = std::getenv("TRPX_PIN_MIN_MB");
+            return (e && *e ? std::size_t(std::strtoull(e, nullptr, 10)) : std::size_t(0)) << 20;
+        }();
+        if (p && min_bytes && bytes >= min_bytes && trpx_host_pin(const_cast<void*>(p), bytes) == TRPX_OK) d_p = const_cast<void*>(p);
+    }
+    ~ScopedPin() { if (d_p) trpx_host_unpin(d_p); }
+    ScopedPin(ScopedPin const&) = delete;
+    ScopedPin& operator=(ScopedPin const&) = delete;
+private:
+    void* d_p = nullptr;
+};
+
+// One grow-only pinned buffer per thread for the payload of an encode call: the worst-case capacity (raw size + 6 %) is
+// never value-initialised (the reference zero-fills it, Terse.hpp:503) and the payload D2H runs at the link rate; only
+// the actual payload is then copied into the object.
+inline std::uint8_t* pinned_scratch(std::size_t bytes)
+{
+    struct Holder {
+        void* p = nullptr;
+        std::size_t cap = 0;
+        ~Holder() { trpx_host_free(p); }
+    };
+    static thread_local Holder h;
+    if (h.cap < bytes) {
+        trpx_host_free(h.p);
+        h.p = trpx_host_alloc(bytes + bytes / 8);
+        h.cap = h.p ? bytes + bytes / 8 : 0;
+    }
+    return static_cast<std::uint8_t*>(h.p);
 }
 
 inline void check(int status, trpx_ctx* ctx)
@@ -267,6 +328,8 @@ public:
     std::size_t terse_size() const { return d_terse_data.size(); }
     unsigned block() const { return d_block; }
     std::uint8_t const* terse_data() const { return d_terse_data.data(); }
+    // shard multi-frame push_back_frames / prolix_frames calls over every visible GPU (default: TRPX_MULTI_GPU, else off)
+    static void use_all_devices(bool on = true) { trpx_detail::multi_gpu() = on; }
 
     // XML element + payload, byte-identical to the reference's writer (Terse.hpp:454-474)
     void write(std::ostream& ostream) const
@@ -311,18 +374,25 @@ private:
             for (std::size_t i = 0; i < n; ++i, ++it) staged.push_back(*it);
             src = staged.data();
         }
-        trpx_ctx* ctx = trpx_detail::context();
+        const bool multi = trpx_detail::multi_gpu() && n_frames > 1;
+        trpx_ctx* ctx = multi ? nullptr : trpx_detail::context();
         const int dt = trpx_detail::dtype_of<V>();
         const std::size_t cap = trpx_max_compressed_bytes(d_size, dt, d_block, n_frames);
-        const std::size_t old = d_terse_data.size();
-        d_terse_data.resize(old + cap);
         std::vector<std::size_t> fb(n_frames);
         std::size_t total = 0;
         unsigned pb = 0;
-        const int rc = trpx_encode_host(ctx, src, dt, d_size, n_frames, d_block, d_terse_data.data() + old, cap, fb.data(), &total, &pb);
-        if (rc != TRPX_OK) d_terse_data.resize(old);
+        int rc;
+        std::uint8_t* scratch = trpx_detail::pinned_scratch(cap);
+        std::vector<std::uint8_t> pageable;                  // (only if the host refuses that much pinned memory)
+        if (!scratch) { pageable.resize(cap); scratch = pageable.data(); }
+        {
+            trpx_detail::ScopedPin pin_in(src, n * sizeof(V));
+            rc = multi ? trpx_pool_encode_host(trpx_detail::pool(), src, dt, d_size, n_frames, d_block, scratch, cap, fb.data(), &total, &pb)
+                       : trpx_encode_host(ctx, src, dt, d_size, n_frames, d_block, scratch, cap, fb.data(), &total, &pb);
+        }
+        if (multi && rc != TRPX_OK) throw std::runtime_error(std::string("trpx_b200: ") + trpx_strerror(rc) + " (" + trpx_pool_last_error(trpx_detail::pool()) + ")");
         trpx_detail::check(rc, ctx);
-        d_terse_data.resize(old + total);
+        d_terse_data.insert(d_terse_data.end(), scratch, scratch + total);
         d_frame_bytes.insert(d_frame_bytes.end(), fb.begin(), fb.end());
         if (pb > d_prolix_bits) d_prolix_bits = pb;
     }
@@ -330,13 +400,23 @@ private:
     void f_decode(void* out, int out_dtype, std::size_t first_frame, std::size_t n_frames)
     {
         if (n_frames == 0) return;
-        trpx_ctx* ctx = trpx_detail::context();
+        const bool multi = trpx_detail::multi_gpu() && n_frames > 1;
+        trpx_ctx* ctx = multi ? nullptr : trpx_detail::context();
         bool known = true;
         for (std::size_t b : d_frame_bytes) known = known && b != 0;
         std::vector<std::size_t> recovered(known ? 0 : d_frame_bytes.size());
-        trpx_detail::check(trpx_decode_host(ctx, d_terse_data.data(), d_terse_data.size(), d_signed ? 1 : 0, d_block, d_size,
-                                            d_frame_bytes.size(), first_frame, n_frames, known ? d_frame_bytes.data() : nullptr,
-                                            known ? nullptr : recovered.data(), out, out_dtype), ctx);
+        int rc;
+        {
+            trpx_detail::ScopedPin pin_in(d_terse_data.data(), d_terse_data.size()), pin_out(out, n_frames * d_size * trpx_dtype_size(out_dtype));
+            rc = multi ? trpx_pool_decode_host(trpx_detail::pool(), d_terse_data.data(), d_terse_data.size(), d_signed ? 1 : 0, d_block, d_size,
+                                               d_frame_bytes.size(), first_frame, n_frames, known ? d_frame_bytes.data() : nullptr,
+                                               known ? nullptr : recovered.data(), out, out_dtype)
+                       : trpx_decode_host(ctx, d_terse_data.data(), d_terse_data.size(), d_signed ? 1 : 0, d_block, d_size,
+                                          d_frame_bytes.size(), first_frame, n_frames, known ? d_frame_bytes.data() : nullptr,
+                                          known ? nullptr : recovered.data(), out, out_dtype);
+        }
+        if (multi && rc != TRPX_OK) throw std::runtime_error(std::string("trpx_b200: ") + trpx_strerror(rc) + " (" + trpx_pool_last_error(trpx_detail::pool()) + ")");
+        trpx_detail::check(rc, ctx);
         if (!known) d_frame_bytes = recovered;               // frame boundaries are cached (absolute, cf. App. C1)
     }
 };

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define TRPX_ABI_VERSION 1
+#define TRPX_ABI_VERSION 2
 
 /* status codes */
 enum {
@@ -41,7 +41,8 @@ enum {
     TRPX_ERR_CUDA = 3,        /* a CUDA runtime call or kernel failed (see trpx_last_error) */
     TRPX_ERR_MALFORMED = 4,   /* payload runs past its end / block counts do not add up */
     TRPX_ERR_NO_DEVICE = 5,   /* no CUDA device: this library has no CPU path */
-    TRPX_ERR_NOMEM = 6        /* device or pinned-host allocation failed */
+    TRPX_ERR_NOMEM = 6,       /* device or pinned-host allocation failed */
+    TRPX_ALREADY = 7          /* trpx_host_pin: the range is pinned already (not an error; do not unpin it) */
 };
 
 /* pixel types: std::is_signed_v of the iterator's value_type decides the stream's signedness
@@ -138,6 +139,42 @@ int trpx_decode_device(trpx_ctx* ctx, int lane, const uint8_t* d_payload, size_t
                        int is_signed, unsigned block, size_t n_values, size_t n_frames,
                        const uint64_t* d_frame_ends, uint64_t* d_frame_ends_out, void* d_out,
                        int out_dtype, uint32_t* d_status, void* stream);
+
+/* ---- several GPUs of one box: ONE stack sharded by frame (Terse.hpp:25-26, :290-302, :505) -- */
+
+/* Frames are independent: `prevbits` restarts per frame (Terse.hpp:505), frames are byte-aligned (:547), and the
+ * only scalars a stack shares are prolix_bits (a max, :516) and memory_size (a sum, :459).  A pool owns one context
+ * and one host thread per device; a call cuts the frames into contiguous ranges, one per device, runs the
+ * single-device host-pointer pipeline on each range concurrently, and concatenates the per-device slabs, frame sizes
+ * and max(prolix_bits) on the host.  There is no collective and no device-to-device traffic.  The results are
+ * byte-identical to the single-device calls. */
+typedef struct trpx_pool trpx_pool;
+/* devices == NULL: every visible CUDA device (n_devices ignored).  TRPX_ERR_NO_DEVICE without a usable GPU. */
+int trpx_pool_create(const int* devices, int n_devices, trpx_pool** pool);
+void trpx_pool_destroy(trpx_pool* pool);
+int trpx_pool_size(const trpx_pool* pool);                    /* number of devices */
+int trpx_pool_device(const trpx_pool* pool, int i);           /* CUDA ordinal of shard i */
+const char* trpx_pool_last_error(const trpx_pool* pool);
+/* Same contract as trpx_encode_host / trpx_decode_host.  trpx_pool_decode_host needs the frame sizes to cut the
+ * payload (frame_bytes != NULL); without them the first device recovers them from the stream first. */
+int trpx_pool_encode_host(trpx_pool* pool, const void* pixels, int dtype, size_t n_values, size_t n_frames,
+                          unsigned block, uint8_t* out, size_t out_capacity, size_t* frame_bytes,
+                          size_t* total_bytes, unsigned* prolix_bits);
+int trpx_pool_decode_host(trpx_pool* pool, const uint8_t* payload, size_t payload_bytes, int is_signed,
+                          unsigned block, size_t n_values, size_t total_frames, size_t first_frame,
+                          size_t n_frames, const size_t* frame_bytes, size_t* frame_bytes_out, void* out,
+                          int out_dtype);
+
+/* ---- pinned host memory for the host-pointer flavours ------------------------------------- */
+
+/* The host-pointer calls copy with cudaMemcpyAsync; from PAGEABLE memory the driver stages every copy through its
+ * own bounce buffer (about a third of the link rate, and the call blocks).  A caller that owns long-lived buffers
+ * pins them once: trpx_host_pin page-locks an existing range (cudaHostRegister), trpx_host_alloc returns pinned
+ * memory.  Both are optional; every entry point accepts pageable pointers. */
+int trpx_host_pin(void* p, size_t bytes);
+int trpx_host_unpin(void* p);
+void* trpx_host_alloc(size_t bytes);
+void trpx_host_free(void* p);
 
 /* ---- introspection (used by bench.py / tests) --------------------------------------------- */
 

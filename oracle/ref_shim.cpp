@@ -214,4 +214,38 @@ double ref_bench_decode(const void* px, int dtype, size_t n, size_t n_frames, un
     return s;
 }
 
+// Byte identity at full scale: per-frame payload size and FNV-1a-64 of the reference's payload bytes (one jpa::Terse
+// per frame, payload = write() minus the XML element), frames partitioned over `threads` threads.  Not timed.
+int ref_frame_digests(const void* px, int dtype, size_t n, size_t n_frames, unsigned threads, uint64_t* sizes,
+                      uint64_t* fnv)
+{
+    if (threads < 1) threads = 1;
+    size_t sz = (dtype & 3) == 0 ? 1 : (dtype & 3) == 1 ? 2 : (dtype & 3) == 2 ? 4 : 8;
+    std::vector<int> bad(threads, 0);
+    std::vector<std::thread> pool;
+    for (unsigned w = 0; w < threads; ++w)
+        pool.emplace_back([&, w] {
+            size_t lo = n_frames * w / threads, hi = n_frames * (w + 1) / threads;
+            for (size_t f = lo; f < hi; ++f)
+                dispatch(dtype, [&](auto* tag) {
+                    using T = std::remove_pointer_t<decltype(tag)>;
+                    jpa::Terse t(reinterpret_cast<const T*>((const uint8_t*)px + f * n * sz), n);
+                    std::ostringstream os;
+                    t.write(os);
+                    const std::string s = os.str();
+                    size_t h = s.find("/>");
+                    if (h == std::string::npos || s.size() - (h + 2) != t.terse_size()) { bad[w] = 1; return 0; }
+                    h += 2;
+                    uint64_t x = 0xcbf29ce484222325ull;
+                    for (size_t i = h; i < s.size(); ++i) { x ^= (uint8_t)s[i]; x *= 0x100000001b3ull; }
+                    sizes[f] = s.size() - h;
+                    fnv[f] = x;
+                    return 0;
+                });
+        });
+    for (auto& th : pool) th.join();
+    for (int b : bad) if (b) return 1;
+    return 0;
+}
+
 } // extern "C"

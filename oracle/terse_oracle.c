@@ -401,3 +401,16 @@ void orc_synth_frame(void* out, int dtype, size_t width, size_t height, double l
         }
     }
 }
+
+/* FNV-1a-64 of each frame of a payload (frame f = bytes [ends[f-1], ends[f])): the checker's side of the full-scale
+ * byte-identity test against the reference's per-frame digests (oracle/ref_shim.cpp: ref_frame_digests). */
+void orc_fnv64_frames(const uint8_t* payload, const uint64_t* ends, size_t n_frames, uint64_t* out)
+{
+    uint64_t b = 0;
+    for (size_t f = 0; f < n_frames; ++f) {
+        uint64_t x = 0xcbf29ce484222325ull;
+        for (uint64_t i = b; i < ends[f]; ++i) { x ^= payload[i]; x *= 0x100000001b3ull; }
+        out[f] = x;
+        b = ends[f];
+    }
+}

@@ -78,6 +78,9 @@ void orc_kat_fill(void* out, int dtype, size_t n, uint64_t seed);
 void orc_synth_frame(void* out, int dtype, size_t width, size_t height, double lambda,
                      unsigned n_peaks, double amp_lo, double amp_hi, uint64_t seed);
 
+/* FNV-1a-64 of each frame of a payload; ends[] are the frames' end byte offsets */
+void orc_fnv64_frames(const uint8_t* payload, const uint64_t* ends, size_t n_frames, uint64_t* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,8 @@ def orc():
                                        C.c_void_p, C.c_int]
         L.orc_frame_widths.restype = C.c_size_t
         L.orc_frame_widths.argtypes = [C.c_void_p, C.c_size_t, C.c_uint, C.c_size_t, C.c_void_p]
+        L.orc_fnv64_frames.restype = None
+        L.orc_fnv64_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.orc_header.restype = C.c_size_t
         L.orc_header.argtypes = [C.c_char_p, C.c_size_t, C.c_uint, C.c_int, C.c_uint, C.c_size_t,
                                  C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t]
@@ -91,6 +93,8 @@ def ref():
         L.ref_prolix.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.ref_close.restype = None
         L.ref_close.argtypes = [C.c_void_p]
+        L.ref_frame_digests.restype = C.c_int
+        L.ref_frame_digests.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_uint, C.c_void_p, C.c_void_p]
         L.ref_bench_encode.restype = C.c_double
         L.ref_bench_encode.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_uint,
                                        C.POINTER(C.c_size_t)]

@@ -27,7 +27,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), n
     assert sorted(names) == sorted(trpx_b200.EXPORTS)
-    assert L.trpx_abi_version() == 1
+    assert L.trpx_abi_version() == 2
 
 
 def test_size_helpers_match_the_oracle():
@@ -59,6 +59,10 @@ def test_no_device_means_no_codec():
     assert L.trpx_ctx_create(0, C.byref(h)) == trpx_b200.ERR_NO_DEVICE
     with pytest.raises(trpx_b200.TrpxError):
         trpx_b200.Codec(0)
+    pool = C.c_void_p()
+    assert L.trpx_pool_create(None, 0, C.byref(pool)) == trpx_b200.ERR_NO_DEVICE     # the multi-GPU entry points too
+    with pytest.raises(trpx_b200.TrpxError):
+        trpx_b200.Pool()
     # null context: every compute entry point refuses
     a = np.zeros(24, np.uint16)
     out = np.zeros(256, np.uint8)

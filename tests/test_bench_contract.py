@@ -23,6 +23,16 @@ def test_reference_arm_prints_one_contract_line():
     assert "workload" in d["config"] and "model" not in d["config"]
 
 
+def test_reference_arm_other_configs():
+    """configs[4] (signed, decode only) through the same arm: the line names its workload and times the decoder alone."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "c5i16", "--steps", "1",
+                        "--warmup", "1", "--frames", "16"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][0])
+    assert d["dtype"] == "i16" and d["config"]["config"] == "c5i16" and d["scaling"] == "strong"
+    assert d["encode_frames_per_s"] is None and d["decode_frames_per_s"] > 0 and d["config"]["same_config"] is True
+
+
 def test_gpu_arm_refuses_to_run_without_cuda():
     try:
         import torch

@@ -22,7 +22,10 @@ EXPORTS = ["trpx_abi_version", "trpx_strerror", "trpx_dtype_size", "trpx_dtype_i
            "trpx_max_compressed_bytes", "trpx_ctx_create", "trpx_ctx_destroy", "trpx_ctx_device",
            "trpx_last_error", "trpx_ctx_lanes", "trpx_ctx_launch_count", "trpx_ctx_scratch_bytes",
            "trpx_encode_host", "trpx_encode_device", "trpx_decode_host", "trpx_decode_device",
-           "trpx_ctx_set_profiling", "trpx_ctx_last_kernel_times", "trpx_ctx_encode_progress"]
+           "trpx_ctx_set_profiling", "trpx_ctx_last_kernel_times", "trpx_ctx_encode_progress",
+           "trpx_pool_create", "trpx_pool_destroy", "trpx_pool_size", "trpx_pool_device", "trpx_pool_last_error",
+           "trpx_pool_encode_host", "trpx_pool_decode_host", "trpx_host_pin", "trpx_host_unpin", "trpx_host_alloc",
+           "trpx_host_free"]
 
 
 class TrpxError(RuntimeError):
@@ -92,6 +95,28 @@ def lib(build_if_missing=True):
     L.trpx_decode_host.argtypes = [vp, vp, sz, i, u, sz, sz, sz, sz, vp, vp, vp, i]
     L.trpx_decode_device.restype = i
     L.trpx_decode_device.argtypes = [vp, i, vp, sz, i, u, sz, sz, vp, vp, vp, i, vp, vp]
+    L.trpx_pool_create.restype = i
+    L.trpx_pool_create.argtypes = [C.POINTER(i), i, C.POINTER(vp)]
+    L.trpx_pool_destroy.restype = None
+    L.trpx_pool_destroy.argtypes = [vp]
+    L.trpx_pool_size.restype = i
+    L.trpx_pool_size.argtypes = [vp]
+    L.trpx_pool_device.restype = i
+    L.trpx_pool_device.argtypes = [vp, i]
+    L.trpx_pool_last_error.restype = C.c_char_p
+    L.trpx_pool_last_error.argtypes = [vp]
+    L.trpx_pool_encode_host.restype = i
+    L.trpx_pool_encode_host.argtypes = [vp, vp, i, sz, sz, u, vp, sz, vp, C.POINTER(sz), C.POINTER(u)]
+    L.trpx_pool_decode_host.restype = i
+    L.trpx_pool_decode_host.argtypes = [vp, vp, sz, i, u, sz, sz, sz, sz, vp, vp, vp, i]
+    L.trpx_host_pin.restype = i
+    L.trpx_host_pin.argtypes = [vp, sz]
+    L.trpx_host_unpin.restype = i
+    L.trpx_host_unpin.argtypes = [vp]
+    L.trpx_host_alloc.restype = vp
+    L.trpx_host_alloc.argtypes = [sz]
+    L.trpx_host_free.restype = None
+    L.trpx_host_free.argtypes = [vp]
     _lib = L
     return L
 
@@ -188,3 +213,64 @@ class Codec:
         self._check(lib().trpx_decode_device(self._h, lane, d_payload, payload_bytes, int(bool(is_signed)), block,
                                              n_values, n_frames, d_frame_ends, d_frame_ends_out, d_out,
                                              dtype_code(out_dtype), d_status, stream))
+
+
+class Pool:
+    """Several GPUs of one box: one stack sharded by frame over them (trpx_pool_*), results concatenated on the host.
+    devices=None takes every visible device."""
+
+    def __init__(self, devices=None):
+        self._h = C.c_void_p()
+        if devices is None:
+            rc = lib().trpx_pool_create(None, 0, C.byref(self._h))
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = lib().trpx_pool_create(arr, len(devices), C.byref(self._h))
+        if rc != OK:
+            raise TrpxError(rc, lib().trpx_strerror(rc).decode())
+
+    def close(self):
+        if self._h:
+            lib().trpx_pool_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def size(self):
+        return int(lib().trpx_pool_size(self._h))
+
+    def _check(self, rc):
+        if rc != OK:
+            detail = lib().trpx_pool_last_error(self._h).decode()
+            raise TrpxError(rc, lib().trpx_strerror(rc).decode() + (": " + detail if detail else ""))
+
+    def encode(self, stack, block=12):
+        stack = np.ascontiguousarray(stack)
+        F, N = stack.shape
+        dt = dtype_code(stack.dtype)
+        cap = lib().trpx_max_compressed_bytes(N, dt, block, F)
+        out = np.empty(cap, np.uint8)
+        fb = np.zeros(F, np.uint64)
+        total = C.c_size_t(0)
+        pb = C.c_uint(0)
+        self._check(lib().trpx_pool_encode_host(self._h, stack.ctypes.data, dt, N, F, block, out.ctypes.data, cap,
+                                                fb.ctypes.data, C.byref(total), C.byref(pb)))
+        return out[:total.value].copy(), fb, pb.value
+
+    def decode(self, payload, n_values, total_frames, is_signed, out_dtype, block=12, frame_bytes=None, first_frame=0,
+               n_frames=None):
+        payload = np.ascontiguousarray(payload, dtype=np.uint8)
+        n_frames = total_frames - first_frame if n_frames is None else n_frames
+        out = np.empty((n_frames, n_values), np.dtype(out_dtype))
+        fb_out = np.zeros(total_frames, np.uint64)
+        fb = None if frame_bytes is None else np.ascontiguousarray(frame_bytes, dtype=np.uint64)
+        self._check(lib().trpx_pool_decode_host(self._h, payload.ctypes.data, payload.size, int(bool(is_signed)), block,
+                                                n_values, total_frames, first_frame, n_frames,
+                                                None if fb is None else fb.ctypes.data, fb_out.ctypes.data,
+                                                out.ctypes.data, dtype_code(out.dtype)))
+        return out, fb_out

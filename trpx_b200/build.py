@@ -73,7 +73,8 @@ def build(force=False, verbose=False):
 ROOT = os.path.dirname(HERE)
 HOST_TARGETS = {"terse_selftest": [os.path.join(ROOT, "cxx", "terse_selftest.cpp")],
                 "terse": [os.path.join(ROOT, "cxx", "terse.cpp")],
-                "prolix": [os.path.join(ROOT, "cxx", "prolix.cpp")]}
+                "prolix": [os.path.join(ROOT, "cxx", "prolix.cpp")],
+                "terse_bench": [os.path.join(ROOT, "cxx", "terse_bench.cpp")]}
 
 
 def build_host(force=False):

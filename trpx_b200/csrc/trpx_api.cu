@@ -12,6 +12,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "codec_launch.cuh"
@@ -91,6 +92,7 @@ struct trpx_ctx {
     u64* h_call_ends = nullptr;        // pinned: frame ends of every batch of one trpx_decode_host call
     size_t h_call_ends_cap = 0;
     DevBuf d_call_status;              // one status word per batch of a trpx_decode_host call
+    DevBuf d_foreign;                  // whole payload of a call that has to recover the frame boundaries first
     EncProgress enc_progress;
     std::vector<u32> call_status;
     u32 coop_grid = 0;
@@ -170,6 +172,18 @@ void walk_geometry(const trpx_ctx* c, u64 payload_bytes, u64 n_frames, u64 nbloc
     const u64 fit = payload_bytes / lanes_wanted / slice * slice;
     if (sg > fit) sg = fit;
     if (sg < slice) sg = slice;
+    // Small calls (a frame or a few: one batch of a few hundred KB) are pure latency: every walker is ONE dependent chain
+    // over warm-up + segment, so both shrink to ~1 KB (a sixth of the usual warm-up; segments may then be shorter than
+    // an unpack slice, whose spare threads idle).  More walkers arrive wrong and are re-walked by the resolve kernel, but
+    // over 1 KB at most.  Measured, one 512x512 frame: 726 -> 200 us (tools/latency_probe.py).
+    if (payload_bytes <= ((u64)8 << 20)) {
+        u64 sw = (w / 6 + 255) / 256 * 256;
+        if (sw < 1024) sw = 1024;
+        if (sw > 8192) sw = 8192;
+        if (payload_bytes > ((u64)256 << 10)) sw *= 2;
+        w = sw;
+        sg = sw;
+    }
     if (!warm) warm = (u32)w;
     if (!seg) seg = (u32)sg;
 }
@@ -245,6 +259,7 @@ const char* trpx_strerror(int s)
     case TRPX_ERR_MALFORMED: return "malformed TERSE payload";
     case TRPX_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU path)";
     case TRPX_ERR_NOMEM: return "out of memory";
+    case TRPX_ALREADY: return "already pinned";
     default: return "unknown status";
     }
 }
@@ -330,6 +345,7 @@ void trpx_ctx_destroy(trpx_ctx* c)
     }
     if (c->h_call_ends) cudaFreeHost(c->h_call_ends);
     if (c->d_call_status.p) cudaFree(c->d_call_status.p);
+    if (c->d_foreign.p) cudaFree(c->d_foreign.p);
     delete c;
 }
 
@@ -554,6 +570,7 @@ int trpx_decode_host(trpx_ctx* c, const uint8_t* payload, size_t payload_bytes, 
 
     // absolute end offsets of every frame
     std::vector<u64> ends(total_frames);
+    const uint8_t* resident = nullptr;                          // device copy of the whole payload, when one exists
     if (frame_bytes) {
         u64 acc = 0;
         for (size_t f = 0; f < total_frames; ++f) { acc += frame_bytes[f]; ends[f] = acc; }
@@ -561,16 +578,18 @@ int trpx_decode_host(trpx_ctx* c, const uint8_t* payload, size_t payload_bytes, 
     } else if (total_frames == 1) {
         ends[0] = payload_bytes;
     } else {
-        // the container does not store frame boundaries (Terse.hpp:459, :562-585): recover them on the device
+        // the container does not store frame boundaries (Terse.hpp:459, :562-585): recover them on the device.  The
+        // payload is uploaded ONCE: it stays resident and the batches below take their slabs from it device-to-device.
         Lane& l = c->lanes[0];
         DecPlan pl = dec_plan(out_dtype, payload_bytes, n_values, total_frames, block, nullptr, 16384, 8192);
         if (!pl.ok) return TRPX_ERR_BAD_ARG;
-        if (!ensure(c, l.d_in, payload_bytes + 16) || !ensure(c, l.d_ends, total_frames * 8)) return TRPX_ERR_NOMEM;
-        if (!cuda_ok(c, cudaMemsetAsync((uint8_t*)l.d_in.p + payload_bytes, 0, 16, l.stream), "memset") ||
-            !cuda_ok(c, cudaMemcpyAsync(l.d_in.p, payload, payload_bytes, cudaMemcpyHostToDevice, l.stream), "H2D payload"))
+        if (!ensure(c, c->d_foreign, payload_bytes + 32) || !ensure(c, l.d_ends, total_frames * 8)) return TRPX_ERR_NOMEM;
+        if (!cuda_ok(c, cudaMemsetAsync((uint8_t*)c->d_foreign.p + (payload_bytes & ~(size_t)15), 0, 32, l.stream), "memset") ||
+            !cuda_ok(c, cudaMemcpyAsync(c->d_foreign.p, payload, payload_bytes, cudaMemcpyHostToDevice, l.stream), "H2D payload"))
             return TRPX_ERR_CUDA;
+        resident = (const uint8_t*)c->d_foreign.p;
         DecParams p{};
-        p.payload = (const u32*)l.d_in.p;
+        p.payload = (const u32*)c->d_foreign.p;
         p.payload_bytes = payload_bytes;
         p.block = block;
         p.n_values = n_values;
@@ -586,7 +605,7 @@ int trpx_decode_host(trpx_ctx* c, const uint8_t* payload, size_t payload_bytes, 
         cudaMemcpyAsync(ends.data(), l.d_ends.p, total_frames * 8, cudaMemcpyDeviceToHost, l.stream);
         cudaMemcpyAsync(l.h_small, l.d_small, 8, cudaMemcpyDeviceToHost, l.stream);
         if (!cuda_ok(c, cudaStreamSynchronize(l.stream), "find frames")) return TRPX_ERR_CUDA;
-        if (l.h_small[1] != 0) return status_of_device_word(l.h_small[1]);
+        if (l.h_small[1] != 0) { note_device_word(c, l.h_small[1]); return status_of_device_word(l.h_small[1]); }
     }
     if (frame_bytes_out)
         for (size_t f = 0; f < total_frames; ++f) frame_bytes_out[f] = (size_t)(ends[f] - (f ? ends[f - 1] : 0));
@@ -631,7 +650,8 @@ int trpx_decode_host(trpx_ctx* c, const uint8_t* payload, size_t payload_bytes, 
         if (!pl.ok) { rc = TRPX_ERR_BAD_ARG; break; }
         if (!ensure(c, l.dec_scratch, pl.scratch_bytes)) { rc = TRPX_ERR_NOMEM; break; }
         cudaMemsetAsync((uint8_t*)l.d_in.p + (slab & ~(size_t)15), 0, 32, l.stream);   // defined bytes after the slab
-        if (!cuda_ok(c, cudaMemcpyAsync(l.d_in.p, payload + slab0, slab, cudaMemcpyHostToDevice, l.stream), "H2D payload") ||
+        if (!cuda_ok(c, resident ? cudaMemcpyAsync(l.d_in.p, resident + slab0, slab, cudaMemcpyDeviceToDevice, l.stream)
+                                 : cudaMemcpyAsync(l.d_in.p, payload + slab0, slab, cudaMemcpyHostToDevice, l.stream), "payload slab") ||
             !cuda_ok(c, cudaMemcpyAsync(l.d_ends.p, h_ends, nf * 8, cudaMemcpyHostToDevice, l.stream), "H2D ends")) {
             rc = TRPX_ERR_CUDA;
             break;
@@ -665,6 +685,188 @@ int trpx_decode_host(trpx_ctx* c, const uint8_t* payload, size_t payload_bytes, 
             if (c->call_status[b] != 0) { note_device_word(c, c->call_status[b]); return status_of_device_word(c->call_status[b]); }
     }
     return rc;
+}
+
+// ------------------------------------------------------------------------------ pinned host memory
+int trpx_host_pin(void* p, size_t bytes)
+{
+    if (!p || !bytes) return TRPX_ERR_BAD_ARG;
+    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return TRPX_ALREADY; }
+    if (e != cudaSuccess) { cudaGetLastError(); return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? TRPX_ERR_NO_DEVICE : TRPX_ERR_NOMEM; }
+    return TRPX_OK;
+}
+
+int trpx_host_unpin(void* p)
+{
+    if (!p) return TRPX_ERR_BAD_ARG;
+    if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return TRPX_ERR_BAD_ARG; }
+    return TRPX_OK;
+}
+
+void* trpx_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (!bytes || cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void trpx_host_free(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------ several devices: frame shards
+struct trpx_pool {
+    std::vector<trpx_ctx*> ctx;
+    std::string last_error;
+};
+
+namespace {
+
+// frames [lo, hi) of shard i out of g: contiguous ranges, the first (n % g) shards one frame longer
+void shard_range(size_t n, size_t g, size_t i, size_t& lo, size_t& hi)
+{
+    const size_t q = n / g, r = n % g;
+    lo = i * q + (i < r ? i : r);
+    hi = lo + q + (i < r ? 1 : 0);
+}
+
+}  // namespace
+
+extern "C" {
+
+int trpx_pool_create(const int* devices, int n_devices, trpx_pool** out)
+{
+    if (!out) return TRPX_ERR_BAD_ARG;
+    *out = nullptr;
+    std::vector<int> devs;
+    if (devices) {
+        if (n_devices <= 0) return TRPX_ERR_BAD_ARG;
+        devs.assign(devices, devices + n_devices);
+    } else {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return TRPX_ERR_NO_DEVICE; }
+        for (int d = 0; d < n; ++d) devs.push_back(d);
+    }
+    trpx_pool* p = new trpx_pool();
+    for (int d : devs) {
+        trpx_ctx* c = nullptr;
+        const int rc = trpx_ctx_create(d, &c);
+        if (rc != TRPX_OK) { trpx_pool_destroy(p); return rc; }
+        p->ctx.push_back(c);
+    }
+    *out = p;
+    return TRPX_OK;
+}
+
+void trpx_pool_destroy(trpx_pool* p)
+{
+    if (!p) return;
+    for (trpx_ctx* c : p->ctx) trpx_ctx_destroy(c);
+    delete p;
+}
+
+int trpx_pool_size(const trpx_pool* p) { return p ? (int)p->ctx.size() : 0; }
+int trpx_pool_device(const trpx_pool* p, int i) { return p && i >= 0 && i < (int)p->ctx.size() ? p->ctx[i]->device : -1; }
+const char* trpx_pool_last_error(const trpx_pool* p) { return p ? p->last_error.c_str() : ""; }
+
+int trpx_pool_encode_host(trpx_pool* p, const void* pixels, int dtype, size_t n_values, size_t n_frames, unsigned block,
+                          uint8_t* out, size_t out_capacity, size_t* frame_bytes, size_t* total_bytes, unsigned* prolix_bits)
+{
+    if (!p || p->ctx.empty()) return TRPX_ERR_BAD_ARG;
+    const size_t sz = dtype_is_pixel(dtype) ? dtype_size(dtype) : 0;
+    if (!pixels || !out || !sz || !block || !n_values || !n_frames) return TRPX_ERR_BAD_ARG;
+    const size_t g = p->ctx.size() < n_frames ? p->ctx.size() : n_frames;
+    if (g == 1) return trpx_encode_host(p->ctx[0], pixels, dtype, n_values, n_frames, block, out, out_capacity, frame_bytes, total_bytes, prolix_bits);
+    // every shard encodes into its own slab (worst-case capacity, pinned when the host grants it); the slabs are then
+    // concatenated in shard order -- the only cross-shard step, and it runs on the host
+    struct Shard { size_t lo = 0, hi = 0, total = 0, cap = 0; unsigned pb = 0; int rc = TRPX_OK; uint8_t* slab = nullptr; bool pinned = false; std::vector<size_t> fb; };
+    std::vector<Shard> sh(g);
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < g; ++i) {
+        Shard& s = sh[i];
+        shard_range(n_frames, g, i, s.lo, s.hi);
+        s.cap = trpx_max_compressed_bytes(n_values, dtype, block, s.hi - s.lo);
+        s.fb.resize(s.hi - s.lo);
+        if (i == 0 && s.cap <= out_capacity) s.slab = out;                         // the first slab is already in place
+        else if ((s.slab = (uint8_t*)trpx_host_alloc(s.cap)) != nullptr) s.pinned = true;
+        else s.slab = (uint8_t*)malloc(s.cap);
+        if (!s.slab) s.rc = TRPX_ERR_NOMEM;
+    }
+    for (size_t i = 0; i < g; ++i)
+        th.emplace_back([&, i] {
+            Shard& s = sh[i];
+            if (s.rc != TRPX_OK) return;
+            s.rc = trpx_encode_host(p->ctx[i], (const uint8_t*)pixels + s.lo * n_values * sz, dtype, n_values, s.hi - s.lo, block,
+                                    s.slab, s.cap, s.fb.data(), &s.total, &s.pb);
+        });
+    for (auto& t : th) t.join();
+    int rc = TRPX_OK;
+    size_t off = 0;
+    unsigned pb = 0;
+    for (size_t i = 0; i < g && rc == TRPX_OK; ++i) {
+        Shard& s = sh[i];
+        if (s.rc != TRPX_OK) { rc = s.rc; p->last_error = "device " + std::to_string(p->ctx[i]->device) + ": " + p->ctx[i]->last_error; break; }
+        if (off + s.total > out_capacity) { rc = TRPX_ERR_CAPACITY; break; }
+        if (s.slab != out + off) memmove(out + off, s.slab, s.total);
+        if (frame_bytes) memcpy(frame_bytes + s.lo, s.fb.data(), s.fb.size() * sizeof(size_t));
+        off += s.total;
+        if (s.pb > pb) pb = s.pb;
+    }
+    for (size_t i = 0; i < g; ++i) {
+        Shard& s = sh[i];
+        if (s.slab && s.slab != out) { if (s.pinned) trpx_host_free(s.slab); else free(s.slab); }
+    }
+    if (rc != TRPX_OK) return rc;
+    if (total_bytes) *total_bytes = off;
+    if (prolix_bits) *prolix_bits = pb;
+    return TRPX_OK;
+}
+
+int trpx_pool_decode_host(trpx_pool* p, const uint8_t* payload, size_t payload_bytes, int is_signed, unsigned block,
+                          size_t n_values, size_t total_frames, size_t first_frame, size_t n_frames, const size_t* frame_bytes,
+                          size_t* frame_bytes_out, void* out, int out_dtype)
+{
+    if (!p || p->ctx.empty()) return TRPX_ERR_BAD_ARG;
+    const size_t so = dtype_size(out_dtype);
+    if (!payload || !payload_bytes || !out || !so || !block || !n_values || !total_frames || !n_frames || first_frame + n_frames > total_frames)
+        return TRPX_ERR_BAD_ARG;
+    const size_t g = p->ctx.size() < n_frames ? p->ctx.size() : n_frames;
+    std::vector<size_t> recovered;
+    if (!frame_bytes && total_frames > 1) {
+        // the container does not store frame boundaries (Terse.hpp:459): the first device recovers them, together with
+        // its own share of the frames; the other shards then know where their slabs start
+        recovered.resize(total_frames);
+        size_t lo, hi;
+        shard_range(n_frames, g, 0, lo, hi);
+        const int rc = trpx_decode_host(p->ctx[0], payload, payload_bytes, is_signed, block, n_values, total_frames, first_frame + lo, hi - lo,
+                                        nullptr, recovered.data(), out, out_dtype);
+        if (rc != TRPX_OK) { p->last_error = p->ctx[0]->last_error; return rc; }
+        frame_bytes = recovered.data();
+        if (frame_bytes_out) memcpy(frame_bytes_out, recovered.data(), total_frames * sizeof(size_t));
+        if (g == 1) return TRPX_OK;
+    } else if (g == 1) {
+        return trpx_decode_host(p->ctx[0], payload, payload_bytes, is_signed, block, n_values, total_frames, first_frame, n_frames, frame_bytes,
+                                frame_bytes_out, out, out_dtype);
+    } else if (frame_bytes_out && frame_bytes) {
+        memcpy(frame_bytes_out, frame_bytes, total_frames * sizeof(size_t));
+    }
+    std::vector<int> rcs(g, TRPX_OK);
+    std::vector<std::thread> th;
+    for (size_t i = recovered.empty() ? 0 : 1; i < g; ++i)
+        th.emplace_back([&, i] {
+            size_t lo, hi;
+            shard_range(n_frames, g, i, lo, hi);
+            rcs[i] = trpx_decode_host(p->ctx[i], payload, payload_bytes, is_signed, block, n_values, total_frames, first_frame + lo, hi - lo,
+                                      frame_bytes, nullptr, (uint8_t*)out + lo * n_values * so, out_dtype);
+        });
+    for (auto& t : th) t.join();
+    for (size_t i = 0; i < g; ++i)
+        if (rcs[i] != TRPX_OK) { p->last_error = "device " + std::to_string(p->ctx[i]->device) + ": " + p->ctx[i]->last_error; return rcs[i]; }
+    return TRPX_OK;
 }
 
 }  // extern "C"
