@@ -299,7 +299,7 @@ class CpuCodec:
             te = 0.0
 
         def dec(f):
-            self.out[f] = orc.decode_frame(self.payloads[f], N, signed, self.px.dtype)
+            self.out[f] = orc.decode_frame(self.payloads[f], N, signed, self.px.dtype)[0]
 
         with ThreadPoolExecutor(self.threads) as ex:
             t0 = time.perf_counter()

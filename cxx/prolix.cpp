@@ -55,6 +55,9 @@ int main(int argc, char const* argv[])
             std::size_t w, h;                                          // no dimensions in the header: a square image
             if (packed.dim().size() < 2) w = h = std::size_t(std::sqrt(double(packed.size())));
             else { w = packed.dim()[0]; h = packed.dim()[1]; }
+            // (the reference truncates or zero-fills silently when w * h differs from the frame size, src/prolix.cpp:61-65,
+            // and deletes the .trpx all the same: here the source is kept whenever the image cannot hold every value)
+            const bool lossless = w * h == packed.size();
             using jpa::tiffio::Kind;
             const unsigned bits = packed.bits_per_val();
             std::vector<jpa::tiffio::Image> stack;
@@ -69,13 +72,24 @@ int main(int argc, char const* argv[])
             rep.user += t_write - t_gpu;
             fs::path target = source;
             target.replace_extension(".tif");
-            std::ofstream out(target, std::ios::binary);
+            fs::path tmp = target;
+            tmp += ".part";
+            std::ofstream out(tmp, std::ios::binary | std::ios::trunc);
             if (!out.is_open()) {
                 std::cerr << "Failed to open tif file " << target << std::endl;
             } else {
                 jpa::tiffio::write(out, stack);
+                const bool wrote = out.good();
+                const std::uintmax_t expect = std::uintmax_t(out.tellp());
                 out.close();
-                fs::remove(source);
+                std::error_code ec;
+                if (!wrote || out.fail() || fs::file_size(tmp, ec) != expect || ec) {     // full disk, quota, I/O error: keep the source
+                    fs::remove(tmp, ec);
+                    throw std::runtime_error("Failed to write the tif file (the trpx file is kept).");
+                }
+                fs::rename(tmp, target);
+                if (lossless) fs::remove(source);
+                else std::cerr << "Frame size " << packed.size() << " is not " << w << " x " << h << ": keeping " << source << std::endl;
                 ++rep.done;
             }
             rep.io += Clock::now() - t_write;

@@ -81,10 +81,23 @@ int main(int argc, char const* argv[])
             trpx_bytes += double(packed.terse_size());
             fs::path target = tif;
             target.replace_extension(".trpx");
-            std::ofstream out(target, std::ios::binary);
+            // The source is the only copy of the data: write to a temporary name, check the stream after the write AND
+            // after the close (a full disk or a quota shows up only there), check the size on disk, rename into place, and
+            // only then delete the TIFF (the reference removes it unconditionally, src/terse.cpp:79-82).
+            fs::path tmp = target;
+            tmp += ".part";
+            std::ofstream out(tmp, std::ios::binary | std::ios::trunc);
             if (!out.is_open()) throw std::runtime_error("Failed to open trpx file for output.");
             packed.write(out);
+            const bool wrote = out.good();
+            const std::uintmax_t expect = std::uintmax_t(out.tellp());
             out.close();
+            std::error_code ec;
+            if (!wrote || out.fail() || fs::file_size(tmp, ec) != expect || ec || expect < packed.terse_size()) {
+                fs::remove(tmp, ec);
+                throw std::runtime_error("Failed to write the trpx file (the TIFF file is kept).");
+            }
+            fs::rename(tmp, target);
             std::cout << "Deleting original TIFF file: " << tif << std::endl;
             fs::remove(tif);
             ++rep.done;

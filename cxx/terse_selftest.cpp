@@ -3,6 +3,7 @@
 // prolix), plus stacks, dims, conversions and error behaviour.
 //   terse_selftest --container <in.trpx> <out.trpx>   host only: read a .trpx, write it back (byte identity is
 //                                                     checked by the caller); prints the parsed attributes
+//   terse_selftest --objects <in> <out>               host only: every <Terse/> object of a stream, read one after another
 //   terse_selftest --gpu                              needs a CUDA device: round trips through the kernels
 #include <cmath>
 #include <cstdio>
@@ -41,6 +42,29 @@ static int container_mode(const char* in, const char* out)
     std::ofstream os(out, std::ios::binary);
     t.write(os);
     return 0;
+}
+
+// host only: a stream may hold several <Terse .../> objects back to back (the reader leaves the stream right after each
+// payload, reference Terse.hpp:275-279, XML_element.hpp:216-224): read them all with consecutive constructor calls and
+// write them back in order.  Malformed headers must throw, never crash.
+static int objects_mode(const char* in, const char* out)
+{
+    std::ifstream is(in, std::ios::binary);
+    std::ofstream os(out, std::ios::binary);
+    int n = 0;
+    for (;;) {
+        try {
+            jpa::Terse t(is);
+            std::printf("object %d: prolix_bits=%u signed=%d block=%u memory_size=%zu number_of_values=%zu frames=%zu\n", n,
+                        t.bits_per_val(), int(t.is_signed()), t.block(), t.terse_size(), t.size(), t.number_of_frames());
+            t.write(os);
+            ++n;
+        } catch (std::exception const& e) {
+            std::printf("stopped after %d object(s): %s\n", n, e.what());
+            break;
+        }
+    }
+    return n ? 0 : 3;
 }
 
 static int tiff_mode(const char* in, const char* out)       // host only: TIFF stack -> TIFF stack through Grey_tiff_io
@@ -122,6 +146,7 @@ int main(int argc, char** argv)
     try {
         if (argc == 4 && !std::strcmp(argv[1], "--container")) return container_mode(argv[2], argv[3]);
         if (argc == 4 && !std::strcmp(argv[1], "--tiff")) return tiff_mode(argv[2], argv[3]);
+        if (argc == 4 && !std::strcmp(argv[1], "--objects")) return objects_mode(argv[2], argv[3]);
         if (argc == 2 && !std::strcmp(argv[1], "--gpu")) return gpu_mode();
     } catch (std::exception const& e) {
         std::printf("exception: %s\n", e.what());

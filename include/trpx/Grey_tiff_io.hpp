@@ -37,7 +37,7 @@ struct Reader {
     bool big;
     std::uint64_t get(std::size_t off, unsigned n) const
     {
-        if (off + n > f.size()) throw std::runtime_error("TIFF: truncated file");
+        if (n > f.size() || off > f.size() - n) throw std::runtime_error("TIFF: truncated file");   // (no overflow in off + n)
         std::uint64_t v = 0;
         for (unsigned i = 0; i < n; ++i) v |= std::uint64_t(f[off + (big ? n - 1 - i : i)]) << (8 * i);
         return v;
@@ -57,6 +57,8 @@ inline std::vector<std::uint64_t> entry_values(Reader const& r, std::size_t e)
     const std::uint64_t count = r.get(e + 4, 4);
     const unsigned ts = type_size(type);
     if (!ts || (type != 1 && type != 3 && type != 4)) throw std::runtime_error("TIFF: unsupported tag type");
+    if (count == 0) throw std::runtime_error("TIFF: tag without a value");
+    if (count > r.f.size()) throw std::runtime_error("TIFF: tag count larger than the file");
     std::size_t off = ts * count <= 4 ? e + 8 : std::size_t(r.get(e + 8, 4));
     std::vector<std::uint64_t> v(count);
     for (std::uint64_t i = 0; i < count; ++i) v[i] = r.get(off + i * ts, ts);
@@ -81,7 +83,12 @@ inline std::vector<Image> read(std::istream& in)
     if (r.get(2, 2) != 42) throw std::runtime_error("TIFF: not a classic TIFF (BigTIFF is not supported)");
     std::vector<Image> images;
     std::size_t ifd = std::size_t(r.get(4, 4));
+    std::vector<std::size_t> seen;                            // a cyclic chain of IFD offsets must not loop for ever
     while (ifd) {
+        for (std::size_t s : seen)
+            if (s == ifd) throw std::runtime_error("TIFF: cyclic image directory");
+        seen.push_back(ifd);
+        if (seen.size() > f.size() / 14 + 1) throw std::runtime_error("TIFF: more image directories than the file can hold");
         const unsigned n = unsigned(r.get(ifd, 2));
         Image img;
         unsigned compression = 1, spp = 1, fmt = 1;
@@ -107,13 +114,16 @@ inline std::vector<Image> read(std::istream& in)
         img.kind = fmt == 2 ? Kind::Int : fmt == 3 ? Kind::Float : Kind::Uint;
         if (img.kind == Kind::Float && img.bits < 32) throw std::runtime_error("TIFF: unsupported float width");
         if (img.kind != Kind::Float && img.bits == 64) throw std::runtime_error("TIFF: 64-bit integer samples are not supported");
-        const std::size_t bps = img.bits / 8, want = img.pixels() * bps;
+        const std::size_t bps = img.bits / 8;
+        if (img.width == 0 || img.height == 0 || img.width > f.size() || img.height > f.size() / img.width / bps)
+            throw std::runtime_error("TIFF: image larger than the file");   // (also keeps width * height * bps from overflowing)
+        const std::size_t want = img.pixels() * bps;
         img.data.resize(want);
         std::size_t got = 0;
         for (std::size_t s = 0; s < offs.size() && got < want; ++s) {
             std::size_t cnt = s < counts.size() ? std::size_t(counts[s]) : want - got;
             if (cnt > want - got) cnt = want - got;
-            if (offs[s] + cnt > f.size()) throw std::runtime_error("TIFF: strip outside the file");
+            if (cnt > f.size() || offs[s] > f.size() - cnt) throw std::runtime_error("TIFF: strip outside the file");
             std::memcpy(img.data.data() + got, f.data() + offs[s], cnt);
             got += cnt;
         }

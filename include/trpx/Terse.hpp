@@ -14,7 +14,10 @@
 //
 // What differs on purpose: every frame of a multi-frame object decodes correctly
 // (the reference mis-addresses frames >= 2, C1/C2); building a stack is linear, not quadratic (C3);
-// blocks as wide as the type decode correctly (C5); `number_of_frames` may be absent in a header (C8).
+// blocks as wide as the type decode correctly (C5); `number_of_frames` may be absent in a header (C8); an UNSIGNED stream
+// decoded into a SIGNED type keeps its values -- the reference's get_range sign-extends from bit s-1 whenever the
+// OUTPUT type is signed (Bit_pointer.hpp:784-789), so unsigned 5 in a 3-bit block would come back as -3 (C11);
+// malformed headers throw instead of reading garbage.
 // The arithmetic of the codec is NOT here: construction / push_back call trpx_encode_host, prolix
 // calls trpx_decode_host, and both fail (std::runtime_error) when no CUDA device is usable.
 #pragma once
@@ -164,6 +167,16 @@ inline std::string attribute(std::string const& tag, std::string const& name)
     return std::string();
 }
 
+// An unsigned decimal attribute; anything else (absent, empty, a sign, letters, out of range) is a malformed header and
+// throws -- std::stoul alone would read "-3" as a huge value.
+inline unsigned long long parse_unsigned(std::string const& tag, const char* name)
+{
+    const std::string v = attribute(tag, name);
+    if (v.empty() || v.size() > 19 || v.find_first_not_of("0123456789") != std::string::npos)
+        throw std::runtime_error(std::string("trpx: malformed <Terse> header: attribute ") + name);
+    return std::stoull(v);
+}
+
 // Scan forward to "<Terse", return the text up to (not including) the closing '>', leaving the stream on
 // the first payload byte (what XML_element(istream, "Terse") does for the reference, XML_element.hpp:216-224).
 inline bool find_terse_tag(std::istream& in, std::string& tag)
@@ -211,17 +224,22 @@ public:
         std::string tag;
         if (!trpx_detail::find_terse_tag(istream, tag)) throw std::runtime_error("trpx: no <Terse .../> element in stream");
         auto attr = [&](const char* n) { return trpx_detail::attribute(tag, n); };
-        d_prolix_bits = unsigned(std::stoul(attr("prolix_bits")));
-        d_signed = std::stoul(attr("signed")) != 0;
-        d_block = unsigned(std::stoul(attr("block")));
-        d_size = std::stoull(attr("number_of_values"));
+        auto num = [&](const char* n) { return trpx_detail::parse_unsigned(tag, n); };
+        if (tag.empty() || tag.back() != '/') throw std::runtime_error("trpx: malformed <Terse> header: element not closed");
+        d_prolix_bits = unsigned(num("prolix_bits"));
+        d_signed = num("signed") != 0;
+        d_block = unsigned(num("block"));
+        d_size = num("number_of_values");
+        if (d_prolix_bits > 73 || d_block == 0 || d_size == 0) throw std::runtime_error("trpx: malformed <Terse> header");
         std::istringstream dims(attr("dimensions"));
         for (std::size_t v; dims >> v;) d_dim.push_back(v);
-        d_terse_data.resize(std::size_t(std::stold(attr("memory_size"))));
+        d_terse_data.resize(std::size_t(num("memory_size")));
         istream.read(reinterpret_cast<char*>(d_terse_data.data()), std::streamsize(d_terse_data.size()));
         if (std::size_t(istream.gcount()) != d_terse_data.size()) throw std::runtime_error("trpx: truncated TERSE payload");
         const std::string nf = attr("number_of_frames");
-        d_frame_bytes.assign(nf.empty() ? 1 : std::stoull(nf), 0);      // 0: size not known yet
+        const std::size_t frames = nf.empty() ? 1 : std::size_t(num("number_of_frames"));
+        if (frames == 0 || frames > d_terse_data.size()) throw std::runtime_error("trpx: malformed <Terse> header: number_of_frames");
+        d_frame_bytes.assign(frames, 0);                                // 0: size not known yet
         if (d_frame_bytes.size() == 1) d_frame_bytes[0] = d_terse_data.size();
         if (d_block == 0 || d_size == 0) throw std::runtime_error("trpx: malformed <Terse> header");
     }

@@ -122,7 +122,13 @@ int trpx_encode_device(trpx_ctx* ctx, int lane, const void* d_pixels, int dtype,
  * Conversion to out_dtype follows Bit_range::get_range (Bit_pointer.hpp:742-792): values are
  * sign-extended from bit s-1 for signed streams; a block wider than the output type is clamped to
  * the type's range; otherwise the value is truncated.  A signed stream into an unsigned type is
- * TRPX_ERR_BAD_ARG (the reference asserts, Terse.hpp:356-357). */
+ * TRPX_ERR_BAD_ARG (the reference asserts, Terse.hpp:356-357).
+ * Deliberate difference: sign extension follows the STREAM's signedness.  The reference sign-extends whenever the
+ * OUTPUT type is signed (Bit_pointer.hpp:784-789), which turns unsigned 5 in a 3-bit block into -3; here an unsigned
+ * stream decoded into int16 / int32 / int64 keeps its values (tests/test_gpu_parity.py pins this).
+ * `payload` / `d_payload` may be read up to 16 bytes past payload_bytes rounded up to 16 (the device flavour needs
+ * that much capacity behind the payload; the host flavours stage and zero-pad it themselves); those bytes never
+ * influence the result. */
 int trpx_decode_host(trpx_ctx* ctx, const uint8_t* payload, size_t payload_bytes, int is_signed,
                      unsigned block, size_t n_values, size_t total_frames, size_t first_frame,
                      size_t n_frames, const size_t* frame_bytes, size_t* frame_bytes_out, void* out,

@@ -409,3 +409,19 @@ def test_encode_progress_is_a_consistent_prefix(monkeypatch):
         assert all(b == cum[f] for f, b, _, _ in seen)
     finally:
         c.close()
+
+
+def test_unsigned_stream_into_signed_types_keeps_its_values(codec):
+    """Deliberate difference to the reference (trpx_b200.h): sign extension follows the STREAM's signedness, so unsigned
+    data decoded into a signed type -- wider or as wide -- is value preserving; into a narrower signed type it clamps.
+    (The reference's get_range sign-extends whenever the OUTPUT type is signed, Bit_pointer.hpp:784-789.)"""
+    a = np.array([5, 7, 4, 6, 5, 7, 4, 6, 5, 7, 4, 6] * 50 + [40000, 65535, 3, 0] * 6, np.uint16)   # top bit of the block width set
+    p, fb, pb = codec.encode(a[None, :])
+    for out in (np.int32, np.int64, np.int16, np.int8):
+        got, _ = codec.decode(p, a.size, 1, False, out, frame_bytes=fb)
+        want, used = orc.decode_frame(p, a.size, False, out)
+        assert np.array_equal(got[0], want)
+        if np.dtype(out).itemsize > 2:
+            assert np.array_equal(got[0], a.astype(out))                 # nothing turns negative
+    got16, _ = codec.decode(p, a.size, 1, False, np.int16, frame_bytes=fb)
+    assert got16[0][600] == np.int16(-25536) and got16[0][0] == 5       # same-width: the documented wrap (Terse.hpp:113-115)
