@@ -759,12 +759,51 @@ def run_e2e(a, cfg, torch, np, trpx_b200, codec, dist, dev, local, rank, world, 
         ts = sorted(float(x) for x in t.cpu())
         return ts[len(ts) // 2] if len(ts) % 2 else 0.5 * (ts[len(ts) // 2 - 1] + ts[len(ts) // 2]), ts
 
+    # ---- what this box can move: every rank copies the SAME bytes the sequential e2e moves, at the same time, with
+    # plain large pinned copies and no codec at all.  (At N = 8 the ranks share one host's memory and PCIe roots: the
+    # e2e number is then a fraction of this ceiling, not of 8 x the single-GPU link rate.)
+    def host_ceiling():
+        big = 128 << 20
+        scratch = torch.empty(min(raw_e, 1 << 30), dtype=torch.uint8, device=dev)
+        hp, hb = h_px.view(torch.uint8).reshape(-1), h_back.view(torch.uint8).reshape(-1)
+        hpl = h_payload[:cb_e]
+
+        def copy_all(dst_of, src_of, nbytes, h2d):
+            for o in range(0, nbytes, big):
+                n_ = min(big, nbytes - o)
+                if h2d:
+                    scratch[(o % scratch.numel()):(o % scratch.numel()) + n_].copy_(src_of[o:o + n_], non_blocking=True)
+                else:
+                    dst_of[o:o + n_].copy_(scratch[(o % scratch.numel()):(o % scratch.numel()) + n_], non_blocking=True)
+
+        ts = []
+        for k in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            if not decode_only:
+                copy_all(None, hp, raw_e, True)                  # pixels up
+                copy_all(hpl, None, cb_e, False)                 # payload down
+            copy_all(None, hpl, cb_e, True)                      # payload up
+            copy_all(hb, None, raw_e, False)                     # pixels down
+            torch.cuda.synchronize()
+            if k:
+                ts.append(time.perf_counter() - t0)
+        t = torch.tensor([min(ts)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        del scratch
+        return float(t[0])
+
+    ceil_s = host_ceiling()
     seq_s, seq_all = timed(sequential, decode_part_only=decode_only)
     h2d = (0 if decode_only else raw_e) + cb_e + 8 * Fe
     d2h = (0 if decode_only else cb_e) + raw_e + 16 * Fe
     e2e = {"value": e2e_job_frames / seq_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "ms_per_step": 1e3 * seq_s, "uncompressed_GBps": e2e_job_frames * frame_raw / seq_s / 1e9, "frames_per_gpu": Fe,
            "api": ("trpx_decode_host" if decode_only else "trpx_encode_host + trpx_decode_host") + " (pinned host buffers)",
+           "host_ceiling": {"value": e2e_job_frames / ceil_s, "ms_per_step": 1e3 * ceil_s, "e2e_over_ceiling": ceil_s / seq_s,
+                            "how": "all ranks at once copy the bytes the sequential e2e moves (pixels up, payload down, payload up, pixels down) "
+                                   "as plain 128 MB pinned copies, no codec; best of 2, max over ranks"},
            "mode": "sequential", "timing": "median of %d timed passes after one warm-up pass, host clock around the calls" % a.e2e_steps,
            "sequential": {"value": e2e_job_frames / seq_s, "ms_per_step": 1e3 * seq_s, "ms_all_steps": [round(1e3 * x, 2) for x in seq_all],
                           "encode_ms": None if decode_only else 1e3 * min(p_[0] for p_ in seq_parts[1:]),

@@ -93,6 +93,12 @@ struct trpx_ctx {
     size_t h_call_ends_cap = 0;
     DevBuf d_call_status;              // one status word per batch of a trpx_decode_host call
     DevBuf d_foreign;                  // whole payload of a call that has to recover the frame boundaries first
+    // staging of PAGEABLE caller memory (host flavours): helper threads copy chunks into pinned slots, the copy engine
+    // takes them from there (the driver's own bounce path for pageable memory moved ~5 GB/s on the B200 hosts)
+    uint8_t* stage_ring = nullptr;
+    cudaEvent_t stage_ev[6] = {};
+    bool stage_used[6] = {};
+    int stage_threads = 3;             // TRPX_STAGE_THREADS (0: leave pageable copies to the driver)
     EncProgress enc_progress;
     std::vector<u32> call_status;
     u32 coop_grid = 0;
@@ -177,9 +183,8 @@ void walk_geometry(const trpx_ctx* c, u64 payload_bytes, u64 n_frames, u64 nbloc
     // an unpack slice, whose spare threads idle).  More walkers arrive wrong and are re-walked by the resolve kernel, but
     // over 1 KB at most.  Measured, one 512x512 frame: 726 -> 200 us (tools/latency_probe.py).
     if (payload_bytes <= ((u64)8 << 20)) {
-        u64 sw = (w / 6 + 255) / 256 * 256;
-        if (sw < 1024) sw = 1024;
-        if (sw > 8192) sw = 8192;
+        u64 sw = 1024;                                          // the largest power of two <= w / 6, within [1 KB, 8 KB]
+        while (sw < 8192 && 2 * sw <= w / 6) sw *= 2;
         if (payload_bytes > ((u64)256 << 10)) sw *= 2;
         w = sw;
         sg = sw;
@@ -237,6 +242,54 @@ __global__ void publish_results_kernel(const u64* d_ends, u64 n, const u32* d_sm
 }
 
 // device status words: 0, a TRPX_ERR_* code, or >= ST_INTERNAL when a bounded wait inside a kernel ran out (simt.cuh)
+constexpr size_t STAGE_CHUNK = 8u << 20;
+
+bool is_pageable(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+// Host -> device copy on `stream`.  Pinned sources go straight to the copy engine.  Pageable sources are cut into
+// 8 MB chunks that helper threads copy into pinned slots (two per thread) and enqueue from there: the host-side
+// memcpy of one chunk overlaps the DMA of the others.  Returns when every chunk has been ENQUEUED.
+cudaError_t h2d_async(trpx_ctx* c, void* dst, const void* src, size_t bytes, cudaStream_t stream)
+{
+    const int T = c->stage_threads;
+    if (T <= 0 || bytes < 2 * STAGE_CHUNK || !is_pageable(src)) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
+    if (!c->stage_ring) {
+        if (cudaHostAlloc((void**)&c->stage_ring, 6 * STAGE_CHUNK, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            c->stage_ring = nullptr;
+            return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
+        }
+        for (cudaEvent_t& e : c->stage_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    }
+    const size_t n_chunks = (bytes + STAGE_CHUNK - 1) / STAGE_CHUNK;
+    std::vector<cudaError_t> err((size_t)T, cudaSuccess);
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; ++t)
+        th.emplace_back([&, t] {
+            cudaSetDevice(c->device);
+            size_t k = 0;
+            for (size_t i = (size_t)t; i < n_chunks; i += (size_t)T, ++k) {
+                const int slot = t + T * (int)(k & 1);
+                const size_t off = i * STAGE_CHUNK, n = bytes - off < STAGE_CHUNK ? bytes - off : STAGE_CHUNK;
+                if (c->stage_used[slot]) cudaEventSynchronize(c->stage_ev[slot]);     // the slot's previous chunk has left
+                memcpy(c->stage_ring + (size_t)slot * STAGE_CHUNK, (const uint8_t*)src + off, n);
+                cudaError_t e = cudaMemcpyAsync((uint8_t*)dst + off, c->stage_ring + (size_t)slot * STAGE_CHUNK, n, cudaMemcpyHostToDevice, stream);
+                if (e == cudaSuccess) e = cudaEventRecord(c->stage_ev[slot], stream);
+                c->stage_used[slot] = true;
+                if (e != cudaSuccess) { err[(size_t)t] = e; return; }
+            }
+        });
+    for (auto& x : th) x.join();
+    for (cudaError_t e : err)
+        if (e != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
 int status_of_device_word(u32 w) { return w == 0 ? TRPX_OK : w >= ST_INTERNAL ? TRPX_ERR_CUDA : (int)w; }
 void note_device_word(trpx_ctx* c, u32 w)
 {
@@ -310,6 +363,8 @@ int trpx_ctx_create(int device, trpx_ctx** out)
     c->enc_batch_bytes = getenv("TRPX_ENC_BATCH_MB") ? (size_t)env_u32("TRPX_ENC_BATCH_MB", 0) << 20 : c->batch_bytes;
     c->enc_lanes = (int)env_u32("TRPX_ENC_LANES", (u32)c->enc_lanes);
     c->dec_lanes = (int)env_u32("TRPX_DEC_LANES", (u32)c->dec_lanes);
+    c->stage_threads = (int)env_u32("TRPX_STAGE_THREADS", (u32)c->stage_threads);
+    if (c->stage_threads > 3) c->stage_threads = 3;
     if (c->enc_lanes < 1) c->enc_lanes = 1;
     if (c->enc_lanes > N_LANES) c->enc_lanes = N_LANES;
     if (c->dec_lanes < 1) c->dec_lanes = 1;
@@ -346,6 +401,9 @@ void trpx_ctx_destroy(trpx_ctx* c)
     if (c->h_call_ends) cudaFreeHost(c->h_call_ends);
     if (c->d_call_status.p) cudaFree(c->d_call_status.p);
     if (c->d_foreign.p) cudaFree(c->d_foreign.p);
+    if (c->stage_ring) cudaFreeHost(c->stage_ring);
+    for (cudaEvent_t e : c->stage_ev)
+        if (e) cudaEventDestroy(e);
     delete c;
 }
 
@@ -520,8 +578,7 @@ int trpx_encode_host(trpx_ctx* c, const void* pixels, int dtype, size_t n_values
         EncPlan pl = enc_plan(dtype, l.d_in.p, n_values, nf, block);
         if (!pl.ok) { c->last_error = "unsupported geometry (block too large or too many tiles)"; rc = TRPX_ERR_BAD_ARG; break; }
         if (!ensure(c, l.enc_scratch, pl.scratch_bytes)) { rc = TRPX_ERR_NOMEM; break; }
-        if (!cuda_ok(c, cudaMemcpyAsync(l.d_in.p, (const uint8_t*)pixels + f0 * frame_raw, nf * frame_raw,
-                                        cudaMemcpyHostToDevice, l.stream), "H2D pixels")) { rc = TRPX_ERR_CUDA; break; }
+        if (!cuda_ok(c, h2d_async(c, l.d_in.p, (const uint8_t*)pixels + f0 * frame_raw, nf * frame_raw, l.stream), "H2D pixels")) { rc = TRPX_ERR_CUDA; break; }
         if (l.drain_pending) {                                   // d_out still holds the lane's previous payload
             cudaStreamWaitEvent(l.stream, l.ev_drained, 0);
             l.drain_pending = false;
@@ -651,7 +708,7 @@ int trpx_decode_host(trpx_ctx* c, const uint8_t* payload, size_t payload_bytes, 
         if (!ensure(c, l.dec_scratch, pl.scratch_bytes)) { rc = TRPX_ERR_NOMEM; break; }
         cudaMemsetAsync((uint8_t*)l.d_in.p + (slab & ~(size_t)15), 0, 32, l.stream);   // defined bytes after the slab
         if (!cuda_ok(c, resident ? cudaMemcpyAsync(l.d_in.p, resident + slab0, slab, cudaMemcpyDeviceToDevice, l.stream)
-                                 : cudaMemcpyAsync(l.d_in.p, payload + slab0, slab, cudaMemcpyHostToDevice, l.stream), "payload slab") ||
+                                 : h2d_async(c, l.d_in.p, payload + slab0, slab, l.stream), "payload slab") ||
             !cuda_ok(c, cudaMemcpyAsync(l.d_ends.p, h_ends, nf * 8, cudaMemcpyHostToDevice, l.stream), "H2D ends")) {
             rc = TRPX_ERR_CUDA;
             break;
