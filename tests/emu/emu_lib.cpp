@@ -36,8 +36,9 @@ extern "C" int emu_decode(const uint8_t* payload, size_t payload_bytes, int is_s
     DecPlan pl = dec_plan(out_dtype, payload_bytes, n, frames, block, out, seg_bytes, warm_bytes, sub_shift);
     if (!pl.ok) return 1;
     if (used_staged) *used_staged = pl.staged ? 1 : 0;
-    void* scratch = aligned_alloc(256, pl.scratch_bytes);
-    memset(scratch, 0x5A, pl.scratch_bytes);
+    const size_t need = (dec_scratch_need(pl, out_dtype, payload_bytes, block, frames, frame_ends == nullptr) + 255) / 256 * 256;
+    void* scratch = aligned_alloc(256, need);
+    memset(scratch, 0x5A, need);
     Launcher L{nullptr, 1, nullptr, cudaSuccess};
     decode_async(L, payload, payload_bytes, is_signed != 0, block, n, frames, (const u64*)frame_ends,
                  (u64*)frame_ends_out, out, out_dtype, status, scratch, pl, 1);

@@ -73,6 +73,31 @@ def test_unknown_frame_sizes_are_recovered():
     roundtrip(st[:1], known_ends=False)
 
 
+@pytest.mark.parametrize("seg,warm", [(64, 64), (256, 128), (1024, 512)])
+def test_frame_recovery_follows_the_parallel_walk(seg, warm):
+    """Frame sizes unknown (a foreign .trpx, Terse.hpp:562-585): the payload is walked in parallel as one run of blocks and
+    one warp follows the frames along the checkpoints.  Ragged last blocks (N % 12 != 0), frames shorter than the distance a
+    walker needs to re-synchronise, sparse frames (runs of one-bit headers), wide and signed blocks, many frames."""
+    kw = dict(known_ends=False, seg_bytes=seg, warm_bytes=warm)
+    roundtrip(np.stack([orc.synth_frame(orc.U16, 64, 52, 2.0, 3, 100 + f) for f in range(40)]), **kw)      # 3328 = 277 * 12 + 4
+    roundtrip(np.stack([orc.kat_fill(orc.U16, 30, 5 + f) for f in range(120)]), **kw)                        # tiny frames
+    z = np.zeros((9, 12 * 500 + 7), np.uint8)
+    z[3, 100] = 1
+    z[5, ::97] = 3
+    z[8, -1] = 200
+    roundtrip(z, **kw)                                                                                       # sparse, ragged
+    roundtrip(np.stack([orc.kat_fill(orc.I32, 12 * 77 + 5, 11 + f) for f in range(17)]), **kw)              # wide signed blocks
+    roundtrip(np.stack([orc.kat_fill(orc.U32, 1999, 3 + f) for f in range(6)]), block=7, **kw)              # another block size
+    roundtrip(np.stack([orc.kat_fill(orc.U64, 24, 9 + f) for f in range(30)]), **kw)
+
+
+def test_frame_recovery_flags_a_stream_that_ends_early():
+    st = np.stack([orc.kat_fill(orc.U16, 3000, 7 + f) for f in range(6)])
+    p, per, pb = orc.encode_stack(st)
+    got, status, staged, fe = emu_lib.decode(p[:int(per[:4].sum()) + 10], 3000, 6, False, np.uint16, 12, None, seg_bytes=256, warm_bytes=128)
+    assert status == 4                                       # TRPX_ERR_MALFORMED, no crash, no hang
+
+
 @pytest.mark.parametrize("src,dst", [(np.uint16, np.uint8), (np.uint16, np.uint64), (np.uint16, np.int32),
                                      (np.int16, np.int8), (np.int16, np.int64), (np.uint32, np.uint16),
                                      (np.int32, np.int16), (np.uint8, np.uint32), (np.int64, np.int32)])

@@ -208,7 +208,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // sub_shift: log2 of the checkpoint spacing in bits (8 = 32 bytes ... 5 = 4 bytes; 0 = 32 bytes)
 inline DecPlan dec_plan(int out_dtype, u64 payload_bytes, u64 n_values, u64 n_frames, u32 block,
-                        const void* d_out, u32 seg_bytes, u32 warm_bytes, u32 sub_shift = 0)
+                        const void* d_out, u32 seg_bytes, u32 warm_bytes, u32 sub_shift = 0, bool force_ckpt = false)
 {
     DecPlan pl;
     const size_t so = dtype_size(out_dtype);
@@ -218,7 +218,7 @@ inline DecPlan dec_plan(int out_dtype, u64 payload_bytes, u64 n_values, u64 n_fr
     pl.tiles_per_frame = div_up(pl.nblocks, DEC_TB);
     pl.n_tiles = pl.tiles_per_frame * n_frames;
     if (pl.n_tiles >= (1ull << 31)) pl.ok = false;
-    pl.staged = block == 12 && ((uintptr_t)d_out & 15) == 0 && ((n_values * so) & 15) == 0;
+    pl.staged = force_ckpt || (block == 12 && ((uintptr_t)d_out & 15) == 0 && ((n_values * so) & 15) == 0);
     pl.sub_shift = sub_shift < SUB_SHIFT_MIN || sub_shift > SUB_SHIFT_MAX ? SUB_SHIFT_MAX : sub_shift;
     const u32 sub_bytes = 1u << (pl.sub_shift - 3);
     pl.seg_bytes = (seg_bytes < SUB_BYTES ? SUB_BYTES : seg_bytes + SUB_BYTES - 1) / SUB_BYTES * SUB_BYTES;
@@ -252,6 +252,24 @@ inline DecPlan dec_plan(int out_dtype, u64 payload_bytes, u64 n_values, u64 n_fr
     return pl;
 }
 
+// Frame sizes unknown: the recovery pass (find_frames_async) first uses the scratch for the tables of the G plan --
+// the payload as one frame, checkpoints forced -- and the recovered frame ends sit behind BOTH layouts.
+inline DecPlan dec_plan_chain(const DecPlan& pl, int out_dtype, u64 payload_bytes, u32 block)
+{
+    return dec_plan(out_dtype, payload_bytes, block, 1, block, nullptr, pl.seg_bytes, pl.warm_bytes, pl.sub_shift, true);
+}
+inline size_t dec_chain_ends_offset(const DecPlan& pl, const DecPlan& gpl)
+{
+    return align_up(pl.scratch_bytes > gpl.scratch_bytes ? pl.scratch_bytes : gpl.scratch_bytes, 256);
+}
+// bytes of scratch a decode call needs
+inline size_t dec_scratch_need(const DecPlan& pl, int out_dtype, u64 payload_bytes, u32 block, u64 n_frames, bool frames_unknown)
+{
+    if (!frames_unknown || n_frames <= 1) return pl.scratch_bytes + 256;
+    const DecPlan gpl = dec_plan_chain(pl, out_dtype, payload_bytes, block);
+    return dec_chain_ends_offset(pl, gpl) + align_up(n_frames * 8, 256);
+}
+
 template <typename O, bool SGN>
 inline void unpack_launch_t(Launcher& L, const DecPlan& pl, const DecParams& p)
 {
@@ -280,6 +298,78 @@ inline void unpack_launch(Launcher& L, int out_dtype, const DecPlan& pl, const D
     case DT_F64: unpack_launch_t<double, SGN>(L, pl, p); break;
     default: unpack_launch_t<int64_t, SGN>(L, pl, p); break;
     }
+}
+
+inline void fill_walk_params(DecParams& p, unsigned char* sc, const DecPlan& pl)
+{
+    p.seg_bytes = pl.seg_bytes;
+    p.warm_bytes = pl.warm_bytes;
+    p.max_segs = pl.max_segs;
+    p.seg_base = (u64*)(sc + pl.off_seg_base);
+    p.seg_frame = (u32*)(sc + pl.off_seg_frame);
+    p.seg_entry = (u64*)(sc + pl.off_seg_entry);
+    p.seg_exit = (u64*)(sc + pl.off_seg_exit);
+    p.seg_count = (u32*)(sc + pl.off_seg_count);
+    p.seg_b0 = (u64*)(sc + pl.off_seg_b0);
+    p.changed = (u32*)(sc + pl.off_changed);
+    p.widths = sc + pl.off_widths;
+    p.anchors = (u64*)(sc + pl.off_anchors);
+    p.ckpt = pl.staged ? (u64*)(sc + pl.off_ckpt) : nullptr;
+    p.subs_per_seg = pl.subs_per_seg;
+    p.sub_shift = pl.sub_shift;
+    p.hdr_tab = (unsigned short*)(sc + pl.off_hdr_tab);
+    p.segd = pl.staged ? (u64*)(sc + pl.off_segd) : nullptr;
+}
+
+// Frame boundaries of a payload whose frame sizes are unknown -> d_ends_out[n_frames] (Terse.hpp:562-585).  The whole
+// payload is walked in parallel as ONE run of blocks (speculative walkers + resolve, chain_mode), then one warp follows
+// the frames along the recorded checkpoints (prolix_frame_chain_kernel).  `scratch` holds the tables of
+// dec_plan(.., n_frames = 1, .., force_ckpt = true) -- a prefix of what the call's own plan needs -- and d_ends_out
+// must not overlap them.  Blocks too large for the chain kernel's window fall back to the one-warp walker.
+inline void find_frames_async(Launcher& L, const void* d_payload, u64 payload_bytes, u32 block, u64 nblocks, u32 last_cnt,
+                              u64 n_frames, u64* d_ends_out, u32* d_status, void* scratch, const DecPlan& gpl, u32 coop_grid)
+{
+    unsigned char* sc = (unsigned char*)scratch;
+    DecParams p{};
+    p.payload = (const u32*)d_payload;
+    p.payload_bytes = payload_bytes;
+    p.block = block;
+    p.nblocks = nblocks;
+    p.last_cnt = last_cnt;
+    p.status = d_status;
+    if (12 + (u64)block * 73 + 64 > (u64)FC_CHUNK_WORDS * 32 || !gpl.staged) {
+        p.n_frames = n_frames;
+        L.err = launch(prolix_find_frames_kernel, 1u, 32u, 0, L.stream, p, d_ends_out);
+        L.count("prolix_find_frames");
+        return;
+    }
+    // G: the payload as one frame of (arbitrarily many) full blocks
+    fill_walk_params(p, sc, gpl);
+    p.chain_mode = 1;
+    p.n_frames = 1;
+    p.n_values = 0;
+    p.nblocks = ~0ull >> 2;
+    u64* g_end = (u64*)(sc + gpl.off_frame_ends);
+    cudaMemsetAsync(sc + gpl.off_zero_begin, 0, 256, L.stream);
+    L.err = launch(prolix_single_frame_kernel, 1u, 32u, 0, L.stream, g_end, payload_bytes);
+    if (L.err != cudaSuccess) return;
+    p.frame_ends = g_end;
+    L.err = launch(prolix_segments_kernel<SEGTAB_NT>, 1u, (u32)SEGTAB_NT, 0, L.stream, p);
+    L.count("prolix_segments");
+    if (L.err != cudaSuccess) return;
+    const u32 walk_grid = (u32)div_up(gpl.max_segs, WALK_NT);
+    const size_t walk_smem = HDR_TAB_BYTES + (size_t)(WALK_NT / 32) * WALK_BUF_WORDS * 4;
+    L.err = launch(prolix_walk_kernel<WALK_NT>, walk_grid, (u32)WALK_NT, walk_smem, L.stream, p);
+    L.count("prolix_walk");
+    if (L.err != cudaSuccess) return;
+    L.err = launch_coop(prolix_resolve_kernel<RESOLVE_NT>, coop_grid, (u32)RESOLVE_NT, 0, L.stream, p);
+    L.count("prolix_resolve");
+    if (L.err != cudaSuccess) return;
+    // T: follow the frames
+    p.n_frames = n_frames;
+    p.nblocks = nblocks;
+    L.err = launch(prolix_frame_chain_kernel, 1u, 32u, 0, L.stream, p, d_ends_out);
+    L.count("prolix_frame_chain");
 }
 
 // d_frame_ends == nullptr: recover the frame boundaries from the stream first (and report them in
@@ -330,10 +420,15 @@ inline void decode_async(Launcher& L, const void* d_payload, u64 payload_bytes, 
         if (n_frames == 1) {
             // a single frame ends where the payload ends; nothing to search for
             L.err = launch(prolix_single_frame_kernel, 1u, 32u, 0, L.stream, fe, payload_bytes);
+            L.count("prolix_find_frames");
         } else {
-            L.err = launch(prolix_find_frames_kernel, 1u, 32u, 0, L.stream, p, fe);
+            // (the G tables come first in the scratch, the call's own tables are written over them afterwards; the
+            // recovered ends sit behind both: dec_scratch_need())
+            const DecPlan gpl = dec_plan_chain(pl, out_dtype, payload_bytes, block);
+            if (!d_frame_ends_out) fe = (u64*)(sc + dec_chain_ends_offset(pl, gpl));
+            find_frames_async(L, d_payload, payload_bytes, block, pl.nblocks, pl.last_cnt, n_frames, fe, d_status, scratch, gpl, coop_grid);
+            cudaMemsetAsync(sc + pl.off_zero_begin, 0, pl.staged ? 256 : pl.scratch_bytes - pl.off_zero_begin, L.stream);
         }
-        L.count("prolix_find_frames");
         if (L.err != cudaSuccess) return;
         d_frame_ends = fe;
     }

@@ -61,6 +61,7 @@ struct DecParams {
     u64 tiles_per_frame;
     void* out;
     u32* status;            // [1]
+    u32 chain_mode;         // frame recovery: the payload is walked as ONE run of blocks (no frame structure known yet)
 };
 
 constexpr u32 DEC_MALFORMED = 4;   // == TRPX_ERR_MALFORMED
@@ -721,7 +722,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_resolve_kernel(DecParams p)
             if (t == 0) sm_run += total;
             sync_block();
         }
-        if (t == 0 && sm_run < p.nblocks) atomic_max(p.status, DEC_MALFORMED);   // stream ends early
+        if (t == 0 && sm_run < p.nblocks && !p.chain_mode) atomic_max(p.status, DEC_MALFORMED);   // stream ends early
         sync_block();
     }
 }
@@ -1380,6 +1381,147 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(UNP_NT, UNP_CTAS) prolix_unpack_seg_kernel(D
 TRPX_KERNEL void prolix_single_frame_kernel(u64* frame_ends_out, u64 payload_bytes)
 {
     if (bid() == 0 && tid() == 0) frame_ends_out[0] = payload_bytes;
+}
+
+// ------------------------------------------------------------------ frame sizes unknown, fast path
+// The .trpx header stores only the total payload size (Terse.hpp:459), so the frame boundaries of a foreign stack have
+// to be recovered from the stream (the reference walks every header of every earlier frame, Terse.hpp:562-585).  Here:
+//   1. the speculative walkers + resolve kernel above parse the WHOLE payload as one run of full blocks, ignoring
+//      frames ("G"): exact checkpoints (position, carried width, header count) every sub-segment, in parallel.
+//   2. the true parse ("T") differs from G only near frame boundaries -- the last block of a frame may be ragged, the
+//      frame is padded to whole bytes, the width restarts at 0 -- and G, being self-synchronising, is back on the true
+//      chain a few hundred bytes later.  So ONE warp follows the frames: from a frame's start it walks T until T meets
+//      one of G's checkpoints (same position, same carried width or an explicit header), then JUMPS: the frame's last
+//      block is G's header number (G's count at the meeting point) + (blocks of the frame still to go), found by a
+//      search over the segment counts and one checkpoint row, a handful of steps from there.
+// Per frame that is ~100 header steps in shared memory and three look-ups instead of a walk over all its blocks
+// (21 846 for a 512 x 512 frame).  The chain over frames itself stays serial: where frame f+1 starts is only known once
+// frame f has been followed to its end.
+constexpr u32 FC_CHUNK_WORDS = 1024;                       // stream staged per refill: 4 KB
+struct ChainWin {                                          // one warp's window on the stream
+    u32* chunk;
+    u64 chunk_bit;                                         // absolute bit of chunk[0] (multiple of 128); ~0: nothing staged
+    TRPX_DEVICE void need(const DecParams& p, u64 n_words, u64 abit, u32 span_bits)      // all lanes
+    {
+        if (chunk_bit != ~0ull && abit >= chunk_bit && abit - chunk_bit + span_bits + 64 <= (u64)FC_CHUNK_WORDS * 32) return;
+        sync_warp();
+        chunk_bit = abit & ~127ull;
+        const u64 w0 = chunk_bit >> 5;
+        for (u32 i = tid() & 31; i < FC_CHUNK_WORDS + 4; i += 32) chunk[i] = w0 + i < n_words ? p.payload[w0 + i] : 0u;
+        sync_warp();
+    }
+    TRPX_DEVICE u32 peek(u64 abit) const                    // >= 32 - 0 valid bits from abit (inside the staged window)
+    {
+        const u32 q = (u32)(abit - chunk_bit);
+        return funnel_r(chunk[q >> 5], chunk[(q >> 5) + 1], q & 31);
+    }
+};
+
+TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(32, 1) prolix_frame_chain_kernel(DecParams p, u64* frame_ends_out)
+{
+    TRPX_SHARED u32 chunk[FC_CHUNK_WORDS + 4];
+    if (bid() != 0) return;
+    const u32 lane = tid() & 31;
+    const u64 n_words = (p.payload_bytes + 3) >> 2;
+    const u64 total_bits = p.payload_bytes * 8;
+    const u64 n_segs = p.seg_base[1];                       // G: one "frame" = the whole payload
+    const u64 seg_bits = (u64)p.seg_bytes * 8;
+    const u32 subs = p.subs_per_seg, sh = p.sub_shift;
+    const u64 max_block_bits = 12 + (u64)p.block * 73;
+    ChainWin win;
+    win.chunk = chunk;
+    win.chunk_bit = ~0ull;
+    u64 P = 0;                                              // absolute bit at which the frame starts (byte aligned)
+    bool bad = max_block_bits + 64 > (u64)FC_CHUNK_WORDS * 32;   // (huge blocks: the caller uses the plain walker instead)
+    for (u64 f = 0; f < p.n_frames; ++f) {
+        // ---- T from the frame start until it meets G (or the frame ends first: tiny frames)
+        u64 pos = P;
+        u32 s = 0;
+        u64 c = 0;                                          // headers of this frame before `pos`
+        u64 next_sub = ~0ull;                               // first bit of the next sub-segment boundary to check
+        bool met = false;
+        u64 g_idx = 0;                                      // G's number of the header at `pos` when met
+        while (!bad && c + 1 < p.nblocks && !met) {
+            if (pos >= total_bits) { bad = true; break; }
+            // is `pos` the first header at or after a sub-segment boundary?  then G has a checkpoint to compare with
+            const u64 j = pos / seg_bits;
+            const u32 m = (u32)((pos - j * seg_bits) >> sh);
+            const u64 sub_first = j * seg_bits + ((u64)m << sh);
+            // (every 4th boundary only: a comparison costs a global-memory round trip, a header step in the staged
+            // window a fraction of that)
+            if (j < n_segs && m < subs && (next_sub == ~0ull || sub_first >= next_sub)) {
+                next_sub = (sub_first & ~((4ull << sh) - 1)) + (4ull << sh);
+                const u64 ck = p.ckpt[j * subs + m];
+                win.need(p, n_words, pos, 64);
+                const bool expl = (win.peek(pos) & 1) == 0;
+                if (j * seg_bits + ckpt_rel(ck) == pos && (ckpt_s(ck) == (s & 0xff) || expl)) {
+                    met = true;
+                    g_idx = p.seg_b0[j] + ckpt_n(ck);
+                    break;
+                }
+            }
+            win.need(p, n_words, pos, (u32)max_block_bits);
+            const u32 hl = decode_header((u64)win.peek(pos), s);
+            pos += hl + (u64)s * p.block;
+            ++c;
+        }
+        // ---- jump to the frame's last block along G
+        if (!bad && met && c + 1 < p.nblocks) {
+            const u64 target = g_idx + (p.nblocks - 1 - c);  // G's number of the frame's last header
+            u64 j = pos / seg_bits;
+            for (;;) {                                      // the segment that holds header `target`: 32 candidates per round
+                const u64 jj = j + lane;
+                const bool in = jj < n_segs && p.seg_b0[jj] <= target && target < p.seg_b0[jj] + p.seg_count[jj];
+                const bool past = jj >= n_segs || p.seg_b0[jj] > target;
+                const u32 hit = ballot(in), over = ballot(past);
+                if (hit) { j += (u32)ffs32(hit) - 1; break; }
+                if (over) { bad = true; break; }            // the stream ends before the frame does
+                j += 32;
+            }
+            if (!bad) {
+                const u32 t_local = (u32)(target - p.seg_b0[j]);
+                const u64* row = p.ckpt + j * subs;
+                // the last checkpoint at or before header t_local (checkpoint counts never decrease along a row)
+                u32 lo = 0, n_ck = subs;
+                while (n_ck > 1) {                          // 32-way search
+                    const u32 step = (n_ck + 31) / 32;
+                    const u32 i = lo + lane * step;
+                    const bool ok = lane * step < n_ck && ckpt_n(row[i < subs ? i : subs - 1]) <= t_local;
+                    const u32 okm = ballot(ok);
+                    const u32 k = okm ? 31 - (u32)clz32(okm) : 0;
+                    lo += k * step;
+                    n_ck = n_ck - k * step < step ? n_ck - k * step : step;
+                }
+                const u64 ck = row[lo];
+                if (ckpt_n(ck) > t_local) {
+                    bad = true;                             // (cannot happen: sub-segment 0 counts from 0)
+                } else {
+                    pos = j * seg_bits + ckpt_rel(ck);
+                    s = ckpt_s(ck);
+                    for (u32 k = ckpt_n(ck); k < t_local && !bad; ++k) {     // a few headers at most
+                        if (pos >= total_bits) { bad = true; break; }
+                        win.need(p, n_words, pos, (u32)max_block_bits);
+                        const u32 hl = decode_header((u64)win.peek(pos), s);
+                        pos += hl + (u64)s * p.block;
+                    }
+                    c = p.nblocks - 1;
+                }
+            }
+        }
+        // ---- the frame's last (possibly ragged) block, then the byte padding (Terse.hpp:547)
+        if (!bad) {
+            if (pos >= total_bits) bad = true;
+            else {
+                win.need(p, n_words, pos, 64);
+                const u32 hl = decode_header((u64)win.peek(pos), s);
+                pos += hl + (u64)s * p.last_cnt;
+            }
+        }
+        u64 end = (P >> 3) + 1 + ((pos - P) >> 3);
+        if (bad || end > p.payload_bytes) { if (lane == 0) atomic_max(p.status, DEC_MALFORMED); end = p.payload_bytes; bad = true; }
+        if (lane == 0) frame_ends_out[f] = end;
+        P = end * 8;
+    }
 }
 
 // The chain itself is serial, but one warp walks it co-operatively: the stream is staged in 16 KB

@@ -494,7 +494,7 @@ int trpx_decode_device(trpx_ctx* c, int lane, const uint8_t* d_payload, size_t p
     DecPlan pl = dec_plan(out_dtype, payload_bytes, n_values, n_frames, block, d_out, seg, warm, sub_shift);
     if (!pl.ok) return TRPX_ERR_BAD_ARG;
     Lane& l = c->lanes[lane];
-    if (!ensure(c, l.dec_scratch, pl.scratch_bytes)) return TRPX_ERR_NOMEM;
+    if (!ensure(c, l.dec_scratch, dec_scratch_need(pl, out_dtype, payload_bytes, block, n_frames, d_frame_ends == nullptr))) return TRPX_ERR_NOMEM;
     Launcher L = make_launcher(c, (cudaStream_t)stream, &l);
     decode_async(L, d_payload, payload_bytes, is_signed != 0, block, n_values, n_frames, (const u64*)d_frame_ends,
                  (u64*)d_frame_ends_out, d_out, out_dtype, d_status, l.dec_scratch.p, pl, c->coop_grid);
@@ -638,26 +638,21 @@ int trpx_decode_host(trpx_ctx* c, const uint8_t* payload, size_t payload_bytes, 
         // the container does not store frame boundaries (Terse.hpp:459, :562-585): recover them on the device.  The
         // payload is uploaded ONCE: it stays resident and the batches below take their slabs from it device-to-device.
         Lane& l = c->lanes[0];
-        DecPlan pl = dec_plan(out_dtype, payload_bytes, n_values, total_frames, block, nullptr, 16384, 8192);
-        if (!pl.ok) return TRPX_ERR_BAD_ARG;
-        if (!ensure(c, c->d_foreign, payload_bytes + 32) || !ensure(c, l.d_ends, total_frames * 8)) return TRPX_ERR_NOMEM;
+        u32 seg, warm, sub_shift;
+        const size_t nblocks = (n_values + block - 1) / block;
+        walk_geometry(c, payload_bytes, total_frames, nblocks, seg, warm, sub_shift);
+        const DecPlan gpl = dec_plan(out_dtype, payload_bytes, block, 1, block, nullptr, seg, warm, sub_shift, true);
+        if (!gpl.ok) return TRPX_ERR_BAD_ARG;   // (the batches below know their frame sizes: only this pass needs the G tables)
+        if (!ensure(c, c->d_foreign, payload_bytes + 32) || !ensure(c, l.d_ends, total_frames * 8) || !ensure(c, l.dec_scratch, gpl.scratch_bytes))
+            return TRPX_ERR_NOMEM;
         if (!cuda_ok(c, cudaMemsetAsync((uint8_t*)c->d_foreign.p + (payload_bytes & ~(size_t)15), 0, 32, l.stream), "memset") ||
-            !cuda_ok(c, cudaMemcpyAsync(c->d_foreign.p, payload, payload_bytes, cudaMemcpyHostToDevice, l.stream), "H2D payload"))
+            !cuda_ok(c, h2d_async(c, c->d_foreign.p, payload, payload_bytes, l.stream), "H2D payload"))
             return TRPX_ERR_CUDA;
         resident = (const uint8_t*)c->d_foreign.p;
-        DecParams p{};
-        p.payload = (const u32*)c->d_foreign.p;
-        p.payload_bytes = payload_bytes;
-        p.block = block;
-        p.n_values = n_values;
-        p.n_frames = total_frames;
-        p.nblocks = pl.nblocks;
-        p.last_cnt = pl.last_cnt;
-        p.status = l.d_small + 1;
         cudaMemsetAsync(l.d_small, 0, 8, l.stream);
         Launcher L = make_launcher(c, l.stream);
-        L.err = launch(prolix_find_frames_kernel, 1u, 32u, 0, l.stream, p, (u64*)l.d_ends.p);
-        L.count("prolix_find_frames");
+        find_frames_async(L, c->d_foreign.p, payload_bytes, block, nblocks, (u32)(n_values - (nblocks - 1) * block), total_frames,
+                          (u64*)l.d_ends.p, l.d_small + 1, l.dec_scratch.p, gpl, c->coop_grid);
         if (!cuda_ok(c, L.err, "find frames launch")) return TRPX_ERR_CUDA;
         cudaMemcpyAsync(ends.data(), l.d_ends.p, total_frames * 8, cudaMemcpyDeviceToHost, l.stream);
         cudaMemcpyAsync(l.h_small, l.d_small, 8, cudaMemcpyDeviceToHost, l.stream);
