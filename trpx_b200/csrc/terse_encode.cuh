@@ -25,7 +25,7 @@
 #include "simt.cuh"
 
 #ifndef ENC_UNIT_U8
-#define ENC_UNIT_U8 48
+#define ENC_UNIT_U8 96
 #endif
 #ifndef ENC_UNIT_U32
 #define ENC_UNIT_U32 96
