@@ -433,7 +433,7 @@ inline void decode_async(Launcher& L, const void* d_payload, u64 payload_bytes, 
         d_frame_ends = fe;
     }
     p.frame_ends = d_frame_ends;
-    L.err = launch(prolix_segments_kernel<SEGTAB_NT>, 1u, (u32)SEGTAB_NT, 0, L.stream, p);
+    L.err = launch(prolix_segments_kernel<SEGTAB_NT>, n_frames >= 64 ? 16u : 1u, (u32)SEGTAB_NT, 0, L.stream, p);
     L.count("prolix_segments");
     if (L.err != cudaSuccess) return;
     const u32 walk_grid = (u32)div_up(pl.max_segs, WALK_NT);

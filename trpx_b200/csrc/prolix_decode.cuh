@@ -479,7 +479,7 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_segments_kernel(DecParams p)
 {
     TRPX_SHARED u64 sm_tot[NT / 32];
     const u32 t = tid(), lane = t & 31, warp = t >> 5;
-    build_header_table<NT>(p.hdr_tab);                       // the walkers copy it into shared memory
+    if (bid() == 0) build_header_table<NT>(p.hdr_tab);       // the walkers copy it into shared memory
     // thread t owns the frames [f0, f1): their segment counts, one block-wide scan of the per-thread sums, then
     // the table entries -- one round whatever the number of frames
     const u64 per = div_up(p.n_frames, (u64)NT);
@@ -506,14 +506,17 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_segments_kernel(DecParams p)
         if ((u32)i < warp) base += v;
         total += v;
     }
+    // every CTA of the grid repeats the (cheap) scan; the table entries are shared out frame by frame
     u64 run = base + incl - mine;
     for (u64 f = f0; f < f1; ++f) {
         const u64 nseg = nseg_of(f);
-        p.seg_base[f] = run;
-        for (u64 i = 0; i < nseg && run + i < p.max_segs; ++i) p.seg_frame[run + i] = (u32)f;
+        if (f % nblocks() == bid()) {
+            p.seg_base[f] = run;
+            for (u64 i = 0; i < nseg && run + i < p.max_segs; ++i) p.seg_frame[run + i] = (u32)f;
+        }
         run += nseg;
     }
-    if (t == 0) p.seg_base[p.n_frames] = total > p.max_segs ? p.max_segs : total;
+    if (t == 0 && bid() == 0) p.seg_base[p.n_frames] = total > p.max_segs ? p.max_segs : total;
 }
 
 struct SegInfo { u64 frame, idx, base_bit, frame_bits, r0, r1; };
@@ -536,8 +539,13 @@ TRPX_DEVICE SegInfo seg_info(const DecParams& p, u64 j)
 // right there (a wrong guess self-synchronises with the true chain: SURVEY 7.3; measured distance for
 // 512^2 Poisson frames: median 0.3 KB, 99.9 % < 3 KB), records the state at the first header inside
 // the segment (entry), the state at the first header past its end (exit) and the headers in between.
+// (four 256-thread CTAs per SM = 64 registers per thread: the walk is a dependent chain per lane and is bound by how
+// many chains are in flight, measured 1.17 -> 0.96 ms together with the shorter segments it allows)
+#ifndef WALK_MIN_CTAS
+#define WALK_MIN_CTAS 4
+#endif
 template <int NT>
-TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_walk_kernel(DecParams p)
+TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, WALK_MIN_CTAS) prolix_walk_kernel(DecParams p)
 {
     TRPX_DYN_SMEM(sm);
     unsigned short* tab = (unsigned short*)sm;
@@ -577,6 +585,29 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_walk_kernel(DecParams p)
         p.seg_count[j] = L.n;
     }
 }
+
+// A warp's window on the stream, staged in shared memory with coalesced loads: dependent header steps then cost a
+// shared-memory access each instead of a global-memory round trip (the fix-up below and the frame chain use it; all
+// lanes of the warp execute those walks in lock step, with the same values).
+constexpr u32 FC_CHUNK_WORDS = 1024;                       // stream staged per refill: 4 KB
+struct ChainWin {                                          // one warp's window on the stream
+    u32* chunk;
+    u64 chunk_bit;                                         // absolute bit of chunk[0] (multiple of 128); ~0: nothing staged
+    TRPX_DEVICE void need(const DecParams& p, u64 n_words, u64 abit, u32 span_bits)      // all lanes
+    {
+        if (chunk_bit != ~0ull && abit >= chunk_bit && abit - chunk_bit + span_bits + 64 <= (u64)FC_CHUNK_WORDS * 32) return;
+        sync_warp();
+        chunk_bit = abit & ~127ull;
+        const u64 w0 = chunk_bit >> 5;
+        for (u32 i = tid() & 31; i < FC_CHUNK_WORDS + 4; i += 32) chunk[i] = w0 + i < n_words ? p.payload[w0 + i] : 0u;
+        sync_warp();
+    }
+    TRPX_DEVICE u32 peek(u64 abit) const                    // >= 32 - 0 valid bits from abit (inside the staged window)
+    {
+        const u32 q = (u32)(abit - chunk_bit);
+        return funnel_r(chunk[q >> 5], chunk[(q >> 5) + 1], q & 31);
+    }
+};
 
 // Fix-up of ONE segment whose speculative entry was wrong: re-walk it from the exact state (pos, s), but only
 // until the new trajectory meets the one the walker recorded -- a checkpoint that agrees in (position, carried
@@ -626,6 +657,76 @@ TRPX_DEVICE bool rewalk_until_merged(const DecParams& p, u64 n_words, const SegI
     return false;
 }
 
+// The same re-walk, executed by a WHOLE WARP in lock step (every lane computes the same values; lane 0 stores): the
+// stream comes from the warp's shared-memory window, so a step costs ~a shared-memory access instead of an L2 round
+// trip.  This is what makes short warm-ups affordable: a walker that arrived wrong is put right in microseconds.
+constexpr u32 FIX_ROW_CACHE = 64;                         // checkpoints of the segment staged per refill (512 bytes)
+TRPX_DEVICE bool rewalk_until_merged_warp(const DecParams& p, ChainWin& win, u64* row_cache, u64 n_words, const SegInfo& g, u64 j, u64& pos, u32& s, u32& count)
+{
+    const u32 lane = tid() & 31;
+    u64* row = p.ckpt + j * p.subs_per_seg;
+    u32 cache_base = 0xffffffffu;                            // first entry held in row_cache (a multiple of FIX_ROW_CACHE)
+    // the recorded checkpoint of sub-segment m, through the warp's cache: one coalesced refill per 64 sub-segments
+    // instead of a global-memory round trip every few header steps
+    auto recorded = [&](u32 m) -> u64 {
+        const u32 b = m & ~(FIX_ROW_CACHE - 1);
+        if (b != cache_base) {
+            sync_warp();
+            for (u32 i = lane; i < FIX_ROW_CACHE; i += 32) row_cache[i] = b + i < p.subs_per_seg ? row[b + i] : 0ull;
+            cache_base = b;
+            sync_warp();
+        }
+        return row_cache[m - b];
+    };
+    const u32 subs = p.subs_per_seg, sh = p.sub_shift;
+    const u32 span = 12 + p.block * 73 + 64;
+    const bool windowed = (u64)span + 64 <= (u64)FC_CHUNK_WORDS * 32;       // (huge blocks: straight from global memory)
+    u32 next_m = 0, n = 0;
+    while (pos < g.r1) {
+        u64 win64;
+        if (windowed) {
+            win.need(p, n_words, g.base_bit + pos, span);
+            win64 = (u64)win.peek(g.base_bit + pos) | ((u64)win.peek(g.base_bit + pos + 32) << 32);
+        } else {
+            win64 = peek_bits(p.payload, n_words, g.base_bit + pos);
+        }
+        const u32 rel = (u32)(pos - g.r0);
+        for (const u32 m = rel >> sh; next_m <= m && next_m < subs; ++next_m) {   // this header opens sub-segments next_m .. m
+            const u64 old = recorded(next_m);
+            sync_warp();                                      // every lane has read the old entry: it is rewritten below, either way
+            if (ckpt_rel(old) == rel && ckpt_s(old) == (s & 0xff)) {
+                const u32 delta = n - ckpt_n(old);
+                if (delta)
+                    for (u32 mm = next_m + lane; mm < subs; mm += 32) {          // (the lanes share this sweep of the row)
+                        const u64 c = row[mm];
+                        row[mm] = (c & ~0xffffffffull) | (u64)(u32)((u32)c + delta);
+                    }
+                count = p.seg_count[j] + delta;
+                sync_warp();
+                return true;
+            }
+            if (lane == 0) row[next_m] = pack_ckpt(rel, s, n);
+        }
+        if (s == 0 && (win64 & 1)) {                          // one-bit headers of empty blocks
+            u64 run = (u64)ffs64(~win64 | (1ull << 63)) - 1;
+            if (run > g.r1 - pos) run = g.r1 - pos;
+            const u64 bound = g.r0 + ((u64)next_m << sh);     // the next boundary is a header of this run: stop on it
+            if (next_m < subs && pos + run > bound) run = bound - pos;
+            n += (u32)run;
+            pos += run;
+            continue;
+        }
+        const u32 hl = decode_header(win64, s);
+        pos += hl + (u64)s * p.block;
+        ++n;
+    }
+    if (lane == 0)
+        for (; next_m < subs; ++next_m) row[next_m] = pack_ckpt((u32)(pos - g.r0), s, n);
+    sync_warp();
+    count = n;
+    return false;
+}
+
 // ------------------------------------------------------------------ D2: verify / fix until stable, D3: scan
 // Cooperative launch (whole grid resident): grid_sync() is cooperative_groups' grid barrier on the
 // device and a block barrier in the single-CTA emulator run.
@@ -634,11 +735,15 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_resolve_kernel(DecParams p)
 {
     TRPX_SHARED u64 sm_tot[NT / 32];
     TRPX_SHARED u64 sm_run;
+    TRPX_SHARED u32 sm_win[NT / 32][FC_CHUNK_WORDS + 4];      // one stream window per warp (the fix-up walks)
+    TRPX_SHARED u64 sm_row[NT / 32][FIX_ROW_CACHE];           // ... and its window on the segment's recorded checkpoints
     const u32 t = tid(), lane = t & 31, warp = t >> 5;
     const u64 n_segs = p.seg_base[p.n_frames];
     const u64 n_words = (p.payload_bytes + 3) >> 2;
     const u64 gthreads = (u64)nblocks() * NT, gtid = (u64)bid() * NT + t;
     NoSink ns;
+    ChainWin win;
+    win.chunk = sm_win[warp];
     // ---- fix-up sweeps: entry(j) must equal exit(j-1) (same position; same width unless the header
     // at that position is explicit).  Exact on exit: entry(0) is the frame start, and a sweep without
     // a single rewrite means every segment was walked from its predecessor's recorded exit.
@@ -647,29 +752,53 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_resolve_kernel(DecParams p)
         // or raises until every CTA has passed this sweep's grid barrier
         u32* flag = &p.changed[sweep % 3];
         if (gtid == 0) p.changed[(sweep + 1) % 3] = 0;
-        for (u64 j = gtid; j < n_segs; j += gthreads) {
-            const SegInfo g = seg_info(p, j);
-            if (g.idx == 0) continue;
-            const u64 want = ld_relaxed(&p.seg_exit[j - 1]), have = p.seg_entry[j];
-            bool same = want == have;
-            if (!same && state_pos(want) == state_pos(have))
-                same = (peek_bits(p.payload, n_words, g.base_bit + state_pos(want)) & 1) == 0;
-            if (same) continue;
-            u64 pos = state_pos(want);
-            u32 s = state_s(want);
-            p.seg_entry[j] = want;
-            if (p.ckpt) {                                   // fast path: stop as soon as the recorded trajectory is met
-                u32 count;
-                const bool merged = rewalk_until_merged(p, n_words, g, j, pos, s, count);
-                p.seg_count[j] = count;
-                if (merged) continue;                       // same exit as before: nothing downstream changes
-                st_relaxed(&p.seg_exit[j], pack_state(pos, s));
-            } else {
-                const u64 n = walk_headers(p.payload, n_words, g.base_bit, p.block, pos, s, g.r1, ns);
-                st_relaxed(&p.seg_exit[j], pack_state(pos, s));
-                p.seg_count[j] = n > 0xffffffffull ? 0xffffffffu : (u32)n;
+        // a warp checks 32 consecutive segments at a time (one per lane) and then puts the wrong ones right ONE BY ONE,
+        // all lanes together (rewalk_until_merged_warp)
+        for (u64 base = (gtid - lane); base < n_segs; base += gthreads) {
+            const u64 jl = base + lane;
+            bool fix = false;
+            u64 want = 0;
+            if (jl < n_segs) {
+                const SegInfo gl = seg_info(p, jl);
+                if (gl.idx != 0) {
+                    want = ld_relaxed(&p.seg_exit[jl - 1]);
+                    const u64 have = p.seg_entry[jl];
+                    bool same = want == have;
+                    if (!same && state_pos(want) == state_pos(have))
+                        same = (peek_bits(p.payload, n_words, gl.base_bit + state_pos(want)) & 1) == 0;
+                    fix = !same;
+                }
             }
-            atomic_or(flag, 1u);
+            u32 todo = ballot(fix);
+            while (todo) {
+                const int l = ffs32(todo) - 1;
+                todo &= todo - 1;
+                const u64 j = base + (u64)l;
+                const u64 w = shfl(want, l);
+                const SegInfo g = seg_info(p, j);
+                u64 pos = state_pos(w);
+                u32 s = state_s(w);
+                win.chunk_bit = ~0ull;
+                sync_warp();
+                if (lane == 0) p.seg_entry[j] = w;
+                if (p.ckpt) {                               // fast path: stop as soon as the recorded trajectory is met
+                    u32 count;
+                    const bool merged = rewalk_until_merged_warp(p, win, sm_row[warp], n_words, g, j, pos, s, count);
+                    if (lane == 0) {
+                        p.seg_count[j] = count;
+                        if (!merged) {                      // (merged: same exit as before, nothing downstream changes)
+                            st_relaxed(&p.seg_exit[j], pack_state(pos, s));
+                            atomic_or(flag, 1u);
+                        }
+                    }
+                } else if (lane == 0) {
+                    const u64 n = walk_headers(p.payload, n_words, g.base_bit, p.block, pos, s, g.r1, ns);
+                    st_relaxed(&p.seg_exit[j], pack_state(pos, s));
+                    p.seg_count[j] = n > 0xffffffffull ? 0xffffffffu : (u32)n;
+                    atomic_or(flag, 1u);
+                }
+                sync_warp();
+            }
         }
         grid_sync();
         const u32 any = ld_relaxed(flag);
@@ -1397,26 +1526,6 @@ TRPX_KERNEL void prolix_single_frame_kernel(u64* frame_ends_out, u64 payload_byt
 // Per frame that is ~100 header steps in shared memory and three look-ups instead of a walk over all its blocks
 // (21 846 for a 512 x 512 frame).  The chain over frames itself stays serial: where frame f+1 starts is only known once
 // frame f has been followed to its end.
-constexpr u32 FC_CHUNK_WORDS = 1024;                       // stream staged per refill: 4 KB
-struct ChainWin {                                          // one warp's window on the stream
-    u32* chunk;
-    u64 chunk_bit;                                         // absolute bit of chunk[0] (multiple of 128); ~0: nothing staged
-    TRPX_DEVICE void need(const DecParams& p, u64 n_words, u64 abit, u32 span_bits)      // all lanes
-    {
-        if (chunk_bit != ~0ull && abit >= chunk_bit && abit - chunk_bit + span_bits + 64 <= (u64)FC_CHUNK_WORDS * 32) return;
-        sync_warp();
-        chunk_bit = abit & ~127ull;
-        const u64 w0 = chunk_bit >> 5;
-        for (u32 i = tid() & 31; i < FC_CHUNK_WORDS + 4; i += 32) chunk[i] = w0 + i < n_words ? p.payload[w0 + i] : 0u;
-        sync_warp();
-    }
-    TRPX_DEVICE u32 peek(u64 abit) const                    // >= 32 - 0 valid bits from abit (inside the staged window)
-    {
-        const u32 q = (u32)(abit - chunk_bit);
-        return funnel_r(chunk[q >> 5], chunk[(q >> 5) + 1], q & 31);
-    }
-};
-
 TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(32, 1) prolix_frame_chain_kernel(DecParams p, u64* frame_ends_out)
 {
     TRPX_SHARED u32 chunk[FC_CHUNK_WORDS + 4];

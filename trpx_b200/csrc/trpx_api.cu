@@ -146,8 +146,10 @@ u32 env_u32(const char* name, u32 dflt)
 
 // P1 segment geometry.  A speculative walker needs ~70 blocks (median) to lock onto the true header chain and
 // < ~700 in 99.9 % of the cases (measured on diffraction, sparse and dark-subtracted frames), whatever the block
-// size; so the warm-up is sized in BLOCKS -- 1200 of the stream's mean block size -- and a segment is at least
-// twice the warm-up.  (A walker that still arrives wrong is re-walked by the resolve kernel: slower, never wrong.)
+// size; so the warm-up is sized in BLOCKS -- 600 of the stream's mean block size -- and a segment is 2.5 warm-ups.
+// The ~1 % of walkers that still arrive wrong are re-walked by the resolve kernel, a warp each and from shared
+// memory (never wrong, ~30 us each).  Round 2: 1200 blocks / 16 KB segments -> 600 blocks / 8 KB segments, with four
+// walker CTAs per SM: decode 3.16 -> 3.0 ms per 10,000 frames (sweep in DESIGN.md).
 // Checkpoint spacing: a thread of the unpack kernel owns the blocks whose headers start in one sub-segment; about
 // six blocks per thread keeps its 256-thread slice within one output stage: 32 bytes for diffraction frames
 // (~40 bits per block), down to 4 bytes for sparse counting data (~5 bits per block).
@@ -163,14 +165,14 @@ void walk_geometry(const trpx_ctx* c, u64 payload_bytes, u64 n_frames, u64 nbloc
         while (sub_shift > SUB_SHIFT_MIN && (double)(1u << sub_shift) > 9.0 * mean_bits) --sub_shift;
     }
     if (seg && warm) return;
-    u64 w = (u64)(1200.0 * mean_bits / 8.0);
+    u64 w = (u64)(600.0 * mean_bits / 8.0);
     w = (w + 255) / 256 * 256;
     if (w < 512) w = 512;
     if (w > 131072) w = 131072;
     // a segment: twice the warm-up, in whole slices of the unpack kernel (256 sub-segments); sparse streams get
     // short segments in bytes -- the same ~2400 blocks -- and therefore enough walkers to fill the machine
     const u64 slice = (u64)256 << (sub_shift - 3);
-    u64 sg = (2 * w + slice - 1) / slice * slice;
+    u64 sg = (5 * w / 2 + slice / 2) / slice * slice;        // (to the nearest whole slice)
     // A walker is one dependent chain over warm-up + segment, and a call whose payload gives fewer segments than
     // the machine has lanes for (a few big frames, one batch of a host call) is bound by the length of that chain,
     // not by throughput: then segments shrink towards one slice until ~12 warps of walkers per SM exist.
