@@ -333,29 +333,29 @@ def cpu_model():
 
 
 def synth_stack_cpu(cfg, frames, seed):
-    """CPU-side frames of the config's distribution for the reference arm (no GPU needed): `frames` distinct frames."""
+    """CPU-side frames of the config's distribution for the reference arm (no GPU needed): `frames` DISTINCT frames
+    (a tiled handful of frames would sit in the CPU's caches and flatter the reference)."""
     import numpy as np
-    rng = np.random.default_rng(seed)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc
     H, W = cfg["h"], cfg["w"]
     dt = np.dtype(cfg["dtype"])
     gen = cfg["gen"]
+    rng = np.random.default_rng(seed)
     if gen == "sparse":
         return rng.poisson(0.02, size=(frames, H * W)).astype(dt)
     if gen == "dark":
         return (rng.poisson(3.0, size=(frames, H * W)) - 3 + np.rint(2.0 * rng.standard_normal((frames, H * W)))).astype(dt)
     lam, peaks, amp_hi = (LAMBDA, N_PEAKS, 3000.0) if gen == "bragg" else (0.5, 2000, 1.0e6)
-    img = rng.poisson(lam, size=(frames, H, W)).astype(np.float64)
-    yy, xx = np.mgrid[-4:5, -4:5]
-    for f in range(frames):
-        cy, cx = rng.random(peaks) * (H - 1), rng.random(peaks) * (W - 1)
-        sg = 1.0 + rng.random(peaks)
-        amp = np.exp(math.log(20.0) + rng.random(peaks) * math.log(amp_hi / 20.0))
-        for k in range(peaks):
-            iy, ix = int(round(cy[k])) + yy, int(round(cx[k])) + xx
-            ok = (iy >= 0) & (iy < H) & (ix >= 0) & (ix < W)
-            v = rng.poisson(amp[k] * np.exp(-((iy - cy[k]) ** 2 + (ix - cx[k]) ** 2) / (2 * sg[k] ** 2)))
-            np.add.at(img[f], (iy[ok], ix[ok]), v[ok])
-    return np.clip(img, 0, np.iinfo(dt).max).astype(dt).reshape(frames, H * W)
+    out = np.empty((frames, H * W), dt)
+    from concurrent.futures import ThreadPoolExecutor
+
+    def one(f):                                                     # the oracle's C generator (splitmix64 + inverse-CDF Poisson + peaks)
+        out[f] = orc.synth_frame(orc.code_of(dt), W, H, lam, peaks, seed + f, 20.0, amp_hi)
+
+    with ThreadPoolExecutor(host_cores()) as ex:
+        list(ex.map(one, range(frames)))
+    return out
 
 
 def cpu_sample_frames(a):
@@ -374,16 +374,14 @@ def run_reference(a):
     cfg = a.cfg
     cores = host_cores()
     sample = cpu_sample_frames(a)
-    distinct = min(sample, 64 if cfg["w"] * cfg["h"] <= (1 << 20) else 4)
-    px = synth_stack_cpu(cfg, distinct, 4242)
-    px = np.ascontiguousarray(np.tile(px, (int(math.ceil(sample / px.shape[0])), 1))[:sample])
+    px = synth_stack_cpu(cfg, sample, 4242)
     N = px.shape[1]
     so = px.dtype.itemsize
     codec = CpuCodec(px, cores, cfg["decode_only"])
     te, td = codec.run(max(a.warmup, 1), a.steps)
     v = sample / (te + td)
-    desc = "%d frames (%d distinct synthetic frames of the config's distribution, tiled) per step, %s, %d threads, mean of %d timed steps" % (
-        sample, distinct, "decode only" if cfg["decode_only"] else "encode then decode", cores, a.steps)
+    desc = "%d distinct synthetic frames of the config's distribution per step, %s, %d threads, mean of %d timed steps" % (
+        sample, "decode only" if cfg["decode_only"] else "encode then decode", cores, a.steps)
     line = {
         "impl": "reference", "metric": metric_of(cfg), "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": max(a.warmup, 1), "ms_per_step": 1e3 * (te + td), "higher_is_better": True, "scaling": cfg["scaling"],
