@@ -45,3 +45,15 @@ extern "C" int emu_decode(const uint8_t* payload, size_t payload_bytes, int is_s
     free(scratch);
     return 0;
 }
+
+// batch geometry of the speculative frame chain (tests shrink it to exercise window misses)
+extern "C" void emu_set_spec(unsigned b, unsigned r0, unsigned rs, unsigned max_steps)
+{
+    trpx::g_spec_params[0] = b; trpx::g_spec_params[1] = r0; trpx::g_spec_params[2] = rs; trpx::g_spec_params[3] = max_steps;
+}
+extern "C" unsigned long long emu_spec_followed(int reset)
+{
+    const unsigned long long n = trpx::emu_spec_followed();
+    if (reset) trpx::emu_spec_followed() = 0;
+    return n;
+}

@@ -84,3 +84,15 @@ def decode(payload, n, frames, is_signed, out_dtype, block=12, frame_ends=None, 
                       orc.FLOAT_CODE[npdt] if npdt in orc.FLOAT_CODE else orc.code_of(npdt), st.ctypes.data, seg_bytes, warm_bytes, C.byref(staged), sub_shift)
     assert rc == 0
     return outb.view(npdt).reshape(frames, n).copy(), int(st[0]), bool(staged.value), fe_out
+
+
+def set_spec(b=64, r0=32, rs=80, max_steps=256):
+    """Batch geometry of the speculative frame chain (frames per batch, window radius r0 + rs * sqrt(k), T steps per candidate)."""
+    lib().emu_set_spec(b, r0, rs, max_steps)
+
+
+def spec_followed(reset=True):
+    """Frames whose end the speculative pass produced since the last reset."""
+    L = lib()
+    L.emu_spec_followed.restype = C.c_ulonglong
+    return int(L.emu_spec_followed(1 if reset else 0))

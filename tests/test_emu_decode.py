@@ -89,6 +89,29 @@ def test_frame_recovery_follows_the_parallel_walk(seg, warm):
     roundtrip(np.stack([orc.kat_fill(orc.I32, 12 * 77 + 5, 11 + f) for f in range(17)]), **kw)              # wide signed blocks
     roundtrip(np.stack([orc.kat_fill(orc.U32, 1999, 3 + f) for f in range(6)]), block=7, **kw)              # another block size
     roundtrip(np.stack([orc.kat_fill(orc.U64, 24, 9 + f) for f in range(30)]), **kw)
+    alt = np.stack([orc.synth_frame(orc.U16, 64, 52, 2.0, 3, 300 + f) if f % 3 != 1 else np.zeros(3328, np.uint16) for f in range(14)])
+    roundtrip(alt, **kw)                                     # compressed sizes 50:1 apart: the segment guess overshoots and restarts
+
+
+@pytest.mark.parametrize("spec", [(64, 32, 80, 256), (8, 2, 3, 256), (3, 0, 0, 1), (16, 40, 0, 24)])
+def test_frame_chain_is_followed_speculatively(spec):
+    """The chain over frames as table look-ups: F (the header that ends the next frame) evaluated for windows of candidate
+    headers in parallel, then followed by one thread; window misses end a batch early, frames the candidates cannot decide
+    are left to the serial chain.  Tiny windows force misses and re-anchoring, (3, 0, 0, 1) one exact candidate per frame; a
+    candidate whose T runs out of steps (24, 1) is walked out by the following thread from where it stopped."""
+    emu_lib.set_spec(*spec)
+    try:
+        kw = dict(known_ends=False, seg_bytes=256, warm_bytes=128)
+        emu_lib.spec_followed()
+        roundtrip(np.stack([orc.synth_frame(orc.U16, 128, 104, 2.0, 3, 700 + f) for f in range(12)]), **kw)   # 1110 blocks a frame
+        assert emu_lib.spec_followed() == 12                 # every frame end came from the table, none from the serial chain
+        roundtrip(np.stack([orc.synth_frame(orc.U16, 64, 52, 2.0, 3, 500 + f) for f in range(37)]), **kw)
+        alt = np.stack([orc.synth_frame(orc.U16, 64, 52, 2.0, 3, 300 + f) if f % 3 != 1 else np.zeros(3328, np.uint16) for f in range(14)])
+        roundtrip(alt, **kw)                                 # empty frames: runs of one-bit headers on both sides of a boundary
+        roundtrip(np.stack([orc.kat_fill(orc.I32, 12 * 77 + 5, 11 + f) for f in range(17)]), **kw)
+        roundtrip(np.stack([orc.kat_fill(orc.U16, 12 * 64 + 1, 5 + f) for f in range(21)]), **kw)    # 65 blocks: just above the pass's minimum
+    finally:
+        emu_lib.set_spec()
 
 
 def test_frame_recovery_flags_a_stream_that_ends_early():

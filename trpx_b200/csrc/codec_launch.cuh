@@ -200,7 +200,7 @@ struct DecPlan {
     size_t smem_unpack, off_ckpt, off_hdr_tab, off_segd;
     // scratch layout (byte offsets)
     size_t off_frame_ends, off_seg_base, off_seg_frame, off_seg_entry, off_seg_exit, off_seg_count,
-        off_seg_b0, off_changed, off_zero_begin, off_widths, off_anchors, scratch_bytes;
+        off_seg_b0, off_changed, off_zero_begin, off_widths, off_anchors, off_spec, scratch_bytes;
     bool ok;
 };
 
@@ -248,9 +248,16 @@ inline DecPlan dec_plan(int out_dtype, u64 payload_bytes, u64 n_values, u64 n_fr
         pl.off_anchors = o; o = align_up(o + pl.n_tiles * 8, 256);
         pl.off_widths = o;  o = align_up(o + n_frames * pl.nblocks + 16, 256);
     }
+    pl.off_spec = o;                                         // G plans: the speculative frame chain's state and table
+    if (force_ckpt) o = align_up(o + spec_scratch_bytes(SPEC_B, SPEC_R0, SPEC_RS), 256);
     pl.scratch_bytes = o;
     return pl;
 }
+
+// Batch geometry of the speculative frame chain (frames per batch, window radius R0 + RS * k); the emulator tests
+// shrink it so that window misses and re-anchoring are exercised.  Never larger than the defaults (scratch size).
+inline u32 g_spec_params[4] = {SPEC_B, SPEC_R0, SPEC_RS, SPEC_MAX_STEPS};   // .. and T steps per candidate
+constexpr u64 SPEC_MIN_FRAMES = 4, SPEC_MIN_BLOCKS = 64;
 
 // Frame sizes unknown: the recovery pass (find_frames_async) first uses the scratch for the tables of the G plan --
 // the payload as one frame, checkpoints forced -- and the recovered frame ends sit behind BOTH layouts.
@@ -337,7 +344,7 @@ inline void find_frames_async(Launcher& L, const void* d_payload, u64 payload_by
     p.nblocks = nblocks;
     p.last_cnt = last_cnt;
     p.status = d_status;
-    if (12 + (u64)block * 73 + 64 > (u64)FC_CHUNK_WORDS * 32 || !gpl.staged) {
+    if (12 + (u64)block * 73 + 64 > (u64)FW_WORDS * 32 || !gpl.staged) {
         p.n_frames = n_frames;
         L.err = launch(prolix_find_frames_kernel, 1u, 32u, 0, L.stream, p, d_ends_out);
         L.count("prolix_find_frames");
@@ -365,10 +372,20 @@ inline void find_frames_async(Launcher& L, const void* d_payload, u64 payload_by
     L.err = launch_coop(prolix_resolve_kernel<RESOLVE_NT>, coop_grid, (u32)RESOLVE_NT, 0, L.stream, p);
     L.count("prolix_resolve");
     if (L.err != cudaSuccess) return;
-    // T: follow the frames
+    // T: follow the frames -- speculatively in parallel, then serially whatever that pass left
     p.n_frames = n_frames;
     p.nblocks = nblocks;
-    L.err = launch(prolix_frame_chain_kernel, 1u, 32u, 0, L.stream, p, d_ends_out);
+    u64* spec = nullptr;
+    if (n_frames >= SPEC_MIN_FRAMES && nblocks >= SPEC_MIN_BLOCKS) {
+        spec = (u64*)(sc + gpl.off_spec);
+        const u32 B = g_spec_params[0] < SPEC_B ? g_spec_params[0] : SPEC_B, R0 = g_spec_params[1] < SPEC_R0 ? g_spec_params[1] : SPEC_R0,
+                  RS = g_spec_params[2] < SPEC_RS ? g_spec_params[2] : SPEC_RS;
+        const u32 grid = coop_grid < 2 * (u32)L.sm_count ? coop_grid : 2 * (u32)L.sm_count;   // one candidate per thread
+        L.err = launch_coop(prolix_frame_spec_kernel<SPEC_NT>, grid ? grid : 1u, (u32)SPEC_NT, 0, L.stream, p, d_ends_out, spec, B ? B : 1u, R0, RS, g_spec_params[3] ? g_spec_params[3] : 1u);
+        L.count("prolix_frame_spec");
+        if (L.err != cudaSuccess) return;
+    }
+    L.err = launch(prolix_frame_chain_kernel, 1u, 32u, 0, L.stream, p, d_ends_out, (const u64*)spec);
     L.count("prolix_frame_chain");
 }
 

@@ -1526,44 +1526,94 @@ TRPX_KERNEL void prolix_single_frame_kernel(u64* frame_ends_out, u64 payload_byt
 // Per frame that is ~100 header steps in shared memory and three look-ups instead of a walk over all its blocks
 // (21 846 for a 512 x 512 frame).  The chain over frames itself stays serial: where frame f+1 starts is only known once
 // frame f has been followed to its end.
-TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(32, 1) prolix_frame_chain_kernel(DecParams p, u64* frame_ends_out)
+// The chain's own stream window: 1 KB, refilled by ONE round of independent loads (a frame touches the stream in
+// three places -- its start, the checkpoint before its last block, the last block -- and reads a few hundred
+// bytes at each, so the refill latency, not its size, is what a frame costs).
+constexpr u32 FW_WORDS = 256;
+struct FrameWin {
+    u32* chunk;
+    u64 chunk_bit;                                         // absolute bit of chunk[0] (multiple of 128); ~0: nothing staged
+    TRPX_DEVICE void need(const DecParams& p, u64 n_words, u64 abit, u32 span_bits)      // all lanes
+    {
+        if (chunk_bit != ~0ull && abit >= chunk_bit && abit - chunk_bit + span_bits + 64 <= (u64)FW_WORDS * 32) return;
+        sync_warp();
+        chunk_bit = abit & ~127ull;
+        const u64 w0 = chunk_bit >> 5;
+        const u32 lane = tid() & 31;
+        u32 v[(FW_WORDS + 4 + 31) / 32];
+#pragma unroll
+        for (u32 k = 0; k < (FW_WORDS + 4 + 31) / 32; ++k) {
+            const u32 i = lane + 32 * k;
+            v[k] = (i < FW_WORDS + 4 && w0 + i < n_words) ? p.payload[w0 + i] : 0u;
+        }
+#pragma unroll
+        for (u32 k = 0; k < (FW_WORDS + 4 + 31) / 32; ++k) {
+            const u32 i = lane + 32 * k;
+            if (i < FW_WORDS + 4) chunk[i] = v[k];
+        }
+        sync_warp();
+    }
+    TRPX_DEVICE u32 peek(u64 abit) const
+    {
+        const u32 q = (u32)(abit - chunk_bit);
+        return funnel_r(chunk[q >> 5], chunk[(q >> 5) + 1], q & 31);
+    }
+};
+
+// T: one warp follows the frames along G's checkpoints.  The chain is serial over frames (where frame f + 1 starts
+// is only known once frame f has been followed to its end), so what counts is the number of DEPENDENT global-memory
+// round trips per frame; every step below is one: (1) the stream window at the frame start together with the 32
+// checkpoints that follow it, (2) 32 candidate segments for the frame's last header, starting where the previous
+// frame's span says it will be, (3) that segment's whole checkpoint row, (4) the stream window at the checkpoint.
+// `resume` (may be null): resume[0] = frames whose ends the speculative pass below has already written.
+TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(32, 1) prolix_frame_chain_kernel(DecParams p, u64* frame_ends_out, const u64* resume)
 {
-    TRPX_SHARED u32 chunk[FC_CHUNK_WORDS + 4];
+    TRPX_SHARED u32 chunk[FW_WORDS + 4];
     if (bid() != 0) return;
+    const u64 f_first = resume ? resume[0] : 0;
+    if (f_first >= p.n_frames) return;
     const u32 lane = tid() & 31;
     const u64 n_words = (p.payload_bytes + 3) >> 2;
     const u64 total_bits = p.payload_bytes * 8;
     const u64 n_segs = p.seg_base[1];                       // G: one "frame" = the whole payload
     const u64 seg_bits = (u64)p.seg_bytes * 8;
     const u32 subs = p.subs_per_seg, sh = p.sub_shift;
+    const u64 n_ck = n_segs * subs;
     const u64 max_block_bits = 12 + (u64)p.block * 73;
-    ChainWin win;
+    FrameWin win;
     win.chunk = chunk;
     win.chunk_bit = ~0ull;
-    u64 P = 0;                                              // absolute bit at which the frame starts (byte aligned)
-    bool bad = max_block_bits + 64 > (u64)FC_CHUNK_WORDS * 32;   // (huge blocks: the caller uses the plain walker instead)
-    for (u64 f = 0; f < p.n_frames; ++f) {
+    u64 P = f_first ? frame_ends_out[f_first - 1] * 8 : 0;  // absolute bit at which the frame starts (byte aligned)
+    bool bad = max_block_bits + 64 > (u64)FW_WORDS * 32;    // (huge blocks: the caller uses the plain walker instead)
+    u64 prev_span = 0;                                      // segments the previous frame's jump went forward
+    for (u64 f = f_first; f < p.n_frames; ++f) {
         // ---- T from the frame start until it meets G (or the frame ends first: tiny frames)
         u64 pos = P;
         u32 s = 0;
         u64 c = 0;                                          // headers of this frame before `pos`
-        u64 next_sub = ~0ull;                               // first bit of the next sub-segment boundary to check
         bool met = false;
         u64 g_idx = 0;                                      // G's number of the header at `pos` when met
+        u64 j = pos / seg_bits;                             // segment of `pos`, tracked incrementally
+        u64 seg_first = j * seg_bits;
+        u64 ckq0 = ~0ull, last_q = ~0ull;                   // flat index of lane 0's cached checkpoint / of the last one compared
+        u64 ck_l = ~0ull;
         while (!bad && c + 1 < p.nblocks && !met) {
             if (pos >= total_bits) { bad = true; break; }
-            // is `pos` the first header at or after a sub-segment boundary?  then G has a checkpoint to compare with
-            const u64 j = pos / seg_bits;
-            const u32 m = (u32)((pos - j * seg_bits) >> sh);
-            const u64 sub_first = j * seg_bits + ((u64)m << sh);
-            // (every 4th boundary only: a comparison costs a global-memory round trip, a header step in the staged
-            // window a fraction of that)
-            if (j < n_segs && m < subs && (next_sub == ~0ull || sub_first >= next_sub)) {
-                next_sub = (sub_first & ~((4ull << sh) - 1)) + (4ull << sh);
-                const u64 ck = p.ckpt[j * subs + m];
+            while (pos >= seg_first + seg_bits) { ++j; seg_first += seg_bits; }
+            // G's checkpoint of the sub-segment `pos` lies in names the first header at or after the sub-segment's
+            // first bit: T has met G when that is exactly `pos`, with the same carried width
+            const u32 m = (u32)((pos - seg_first) >> sh);
+            const u64 q = j * subs + m;
+            if (j < n_segs && m < subs && q != last_q) {
+                last_q = q;
+                if (ckq0 == ~0ull || q < ckq0 || q >= ckq0 + 32) {
+                    ckq0 = q;
+                    ck_l = q + lane < n_ck ? p.ckpt[q + lane] : ~0ull;
+                }
+                const u64 ck = shfl(ck_l, (int)(q - ckq0));
                 win.need(p, n_words, pos, 64);
                 const bool expl = (win.peek(pos) & 1) == 0;
-                if (j * seg_bits + ckpt_rel(ck) == pos && (ckpt_s(ck) == (s & 0xff) || expl)) {
+                if (seg_first + ckpt_rel(ck) == pos && (ckpt_s(ck) == (s & 0xff) || expl)) {
                     met = true;
                     g_idx = p.seg_b0[j] + ckpt_n(ck);
                     break;
@@ -1577,35 +1627,44 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(32, 1) prolix_frame_chain_kernel(DecParams p
         // ---- jump to the frame's last block along G
         if (!bad && met && c + 1 < p.nblocks) {
             const u64 target = g_idx + (p.nblocks - 1 - c);  // G's number of the frame's last header
-            u64 j = pos / seg_bits;
+            const u64 j_from = j;
+            u64 j0 = j + (prev_span > 24 ? prev_span - 16 : 0);
             for (;;) {                                      // the segment that holds header `target`: 32 candidates per round
-                const u64 jj = j + lane;
-                const bool in = jj < n_segs && p.seg_b0[jj] <= target && target < p.seg_b0[jj] + p.seg_count[jj];
-                const bool past = jj >= n_segs || p.seg_b0[jj] > target;
+                const u64 jj = j0 + lane;
+                const u64 b0 = jj < n_segs ? p.seg_b0[jj] : ~0ull;
+                const u32 cn = jj < n_segs ? p.seg_count[jj] : 0u;
+                const bool in = jj < n_segs && b0 <= target && target < b0 + cn;
+                const bool past = jj >= n_segs || b0 > target;
                 const u32 hit = ballot(in), over = ballot(past);
-                if (hit) { j += (u32)ffs32(hit) - 1; break; }
+                if (hit) { j = j0 + (u32)ffs32(hit) - 1; break; }
+                if ((over & 1u) && j0 > j_from) { j0 = j_from; continue; }   // guessed too far: search from the start
                 if (over) { bad = true; break; }            // the stream ends before the frame does
-                j += 32;
+                j0 += 32;
             }
             if (!bad) {
+                prev_span = j - j_from;
+                seg_first = j * seg_bits;
                 const u32 t_local = (u32)(target - p.seg_b0[j]);
                 const u64* row = p.ckpt + j * subs;
-                // the last checkpoint at or before header t_local (checkpoint counts never decrease along a row)
-                u32 lo = 0, n_ck = subs;
-                while (n_ck > 1) {                          // 32-way search
-                    const u32 step = (n_ck + 31) / 32;
-                    const u32 i = lo + lane * step;
-                    const bool ok = lane * step < n_ck && ckpt_n(row[i < subs ? i : subs - 1]) <= t_local;
-                    const u32 okm = ballot(ok);
-                    const u32 k = okm ? 31 - (u32)clz32(okm) : 0;
-                    lo += k * step;
-                    n_ck = n_ck - k * step < step ? n_ck - k * step : step;
+                // the last checkpoint at or before header t_local (checkpoint counts never decrease along a row):
+                // every lane reads its share of the row at once
+                const u32 per = (subs + 31) / 32;
+                u64 best = 0;
+                bool any = false;
+#pragma unroll 8
+                for (u32 k = 0; k < per; ++k) {
+                    const u32 i = lane * per + k;
+                    if (i < subs) {
+                        const u64 ck = row[i];
+                        if (ckpt_n(ck) <= t_local) { best = ck; any = true; }
+                    }
                 }
-                const u64 ck = row[lo];
-                if (ckpt_n(ck) > t_local) {
+                const u32 okm = ballot(any);
+                if (!okm) {
                     bad = true;                             // (cannot happen: sub-segment 0 counts from 0)
                 } else {
-                    pos = j * seg_bits + ckpt_rel(ck);
+                    const u64 ck = shfl(best, 31 - clz32(okm));
+                    pos = seg_first + ckpt_rel(ck);
                     s = ckpt_s(ck);
                     for (u32 k = ckpt_n(ck); k < t_local && !bad; ++k) {     // a few headers at most
                         if (pos >= total_bits) { bad = true; break; }
@@ -1631,6 +1690,387 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(32, 1) prolix_frame_chain_kernel(DecParams p
         if (lane == 0) frame_ends_out[f] = end;
         P = end * 8;
     }
+}
+
+// ---- The frame chain, in parallel ----------------------------------------------------------------------------
+// "Frame f ends with G's header e" determines everything about frame f + 1 that the chain needs: the byte the
+// frame ends at, and -- by walking T from the next byte boundary until it meets G -- the number F(e) of G's header
+// that ends frame f + 1.  F does not depend on f, so it can be evaluated for MANY candidate headers at once, one
+// thread each, and the chain itself shrinks to table look-ups: e[f + 1] = F(e[f]).  Frames have nblocks headers
+// each and T and G disagree only over the few dozen headers after a frame boundary, so e[f + k] lies within a few
+// dozen headers per frame of e[f] + k * nblocks: a batch evaluates F on the window of radius R0 + RS * sqrt(k) around
+// that guess for k = 0 .. B - 1 (k = 0 is exact), then one thread follows the chain through the table as far as the
+// windows hold (a miss just ends the batch early; the next batch is centred on the exact value again).  What a
+// thread cannot decide -- frames too short for T to meet G, a stream that ends early -- is left to the serial
+// chain kernel, which resumes where this one stopped.  spec[]: [0] frames done, [1] e of the next frame,
+// [2] segment of the last header located (search hint), [3] segments per frame (hint), [4] stop, [5] headers of G per
+// frame as the last batches saw it (G counts a few dozen headers more than T after every boundary), then the table
+// (next header, end byte, segment) per candidate.
+constexpr u32 SPEC_B = 64, SPEC_R0 = 32, SPEC_RS = 80;      // defaults: ~58,000 candidates per batch of 64 frames
+constexpr u32 SPEC_MAX_STEPS = 256;                         // T steps before a candidate gives up (the chain thread then walks it out)
+constexpr u64 SPEC_INVALID = ~0ull;
+constexpr u32 SPEC_HDR_WORDS = 32;                          // u64 words before the table
+constexpr int SPEC_NT = 256;
+// window radius of the k-th frame of a batch: the disagreement between T and G adds up like a random walk
+TRPX_HD u32 spec_radius(u32 k, u32 r0, u32 rs)
+{
+    const u64 v = (u64)rs * rs * k;
+    u64 r = 0;
+    for (u64 bit = 1ull << 31; bit; bit >>= 1)
+        if ((r | bit) * (r | bit) <= v) r |= bit;
+    return r0 + (u32)r;
+}
+TRPX_HD u64 spec_table_entries(u32 b, u32 r0, u32 rs)
+{
+    u64 n = 0;
+    for (u32 k = 0; k < b; ++k) n += 2 * (u64)spec_radius(k, r0, rs) + 1;
+    return n;
+}
+constexpr u32 SPEC_ENTRY_WORDS = 5;                         // next header, end byte, segment, where T ran out of steps: bit, width | headers << 8
+TRPX_HD size_t spec_scratch_bytes(u32 b, u32 r0, u32 rs) { return (size_t)(SPEC_HDR_WORDS + SPEC_ENTRY_WORDS * spec_table_entries(b, r0, rs)) * 8; }
+
+#ifdef TRPX_EMU
+inline u64& emu_spec_followed() { static u64 n = 0; return n; }   // (tests: frames whose end the speculative pass produced)
+#endif
+struct StreamFifo {                                         // one thread's read-ahead on the stream: four 64-bit words in flight
+    const u64* q;
+    u64 n_q, qi, w0, w1, w2, w3;
+    TRPX_DEVICE void init(const u32* payload, u64 n_words) { q = (const u64*)payload; n_q = (n_words + 1) >> 1; qi = ~0ull - 8; w0 = w1 = w2 = w3 = 0; }
+    TRPX_DEVICE u64 at(u64 i) const { return i < n_q ? q[i] : 0ull; }
+    TRPX_DEVICE u64 peek(u64 abit)                          // 64 valid bits starting at absolute bit `abit`
+    {
+        const u64 i = abit >> 6;
+        const u32 sh = (u32)(abit & 63);
+        if (i != qi) {
+            if (i == qi + 1) { w0 = w1; w1 = w2; w2 = w3; w3 = at(i + 3); }
+            else if (i == qi + 2) { w0 = w2; w1 = w3; w2 = at(i + 2); w3 = at(i + 3); }
+            else { w0 = at(i); w1 = at(i + 1); w2 = at(i + 2); w3 = at(i + 3); }
+            qi = i;
+        }
+        return sh ? (w0 >> sh) | (w1 << (64 - sh)) : w0;
+    }
+};
+
+// F for one candidate: G's header b ends a frame -> the byte that frame ends at (Terse.hpp:547), the header that
+// ends the NEXT frame, and b's segment.  SPEC_INVALID where the answer is the serial chain's business.
+// WARP: the 32 lanes of a warp evaluate 32 candidates together; the function then has NO early exits and every loop
+// runs until the last lane is done with it (a ballot per iteration), so that the lanes stay converged -- lanes left
+// to drift apart through the long T loop execute it one after another.  !WARP: a single thread on its own.
+template <bool WARP>
+TRPX_DEVICE void spec_twalk(const DecParams& p, u64 n_segs, u64 n_words, u64 total_bits, bool ok, u64 max_steps, u64& next, u64& pos_io,
+                            u32& s_io, u64& c_io);
+template <bool WARP>
+TRPX_DEVICE void spec_eval(const DecParams& p, u64 n_segs, u64 n_words, u64 total_bits, u64 total_blocks, bool valid, u64 b, u64 hint,
+                           u64 max_steps, u64& next, u64& endb, u64& jb, u64& cap_state, u64& cap_sc)
+{
+    next = SPEC_INVALID; endb = SPEC_INVALID; jb = 0;
+    bool ok = valid && b < total_blocks;
+    const u64 seg_bits = (u64)p.seg_bytes * 8;
+    const u32 subs = p.subs_per_seg;
+    // ---- b's segment: the last one whose first header number is <= b; gallop from the hint, then bisect
+    u64 lo = 0, hi = 1;
+    if (ok) {
+        const u64 h = hint < n_segs ? hint : n_segs - 1;
+        u64 st = 1;
+        if (p.seg_b0[h] <= b) {
+            lo = h;
+            while (lo + st < n_segs && p.seg_b0[lo + st] <= b) { lo += st; st <<= 1; }
+            hi = lo + st < n_segs ? lo + st : n_segs;
+        } else {
+            hi = h;
+            while (hi > st && p.seg_b0[hi - st] > b) { hi -= st; st <<= 1; }
+            lo = hi > st ? hi - st : 0;
+        }
+        while (hi - lo > 1) {
+            const u64 mid = lo + ((hi - lo) >> 1);
+            if (p.seg_b0[mid] <= b) lo = mid; else hi = mid;
+        }
+    }
+    const u64 j = lo;
+    jb = j;
+    u32 t_local = 0;
+    if (ok) {
+        const u64 t64 = b - p.seg_b0[j];
+        if (t64 >= p.seg_count[j]) ok = false;
+        t_local = (u32)t64;
+    }
+    // ---- the last checkpoint at or before header t_local (counts never decrease along a row; row[0] counts from 0),
+    // the few headers from there to header b, then b's own (possibly ragged) block and the byte padding
+    u64 eb = 0;
+    if (ok) {
+        const u64* row = p.ckpt + j * subs;
+        u32 clo = 0, chi = subs;
+        while (chi - clo > 1) {
+            const u32 mid = clo + ((chi - clo) >> 1);
+            if (ckpt_n(row[mid]) <= t_local) clo = mid; else chi = mid;
+        }
+        const u64 ck0 = row[clo];
+        u64 pos = j * seg_bits + ckpt_rel(ck0);
+        u32 s = ckpt_s(ck0);
+        ok = ckpt_n(ck0) <= t_local;
+        StreamFifo fifo;
+        fifo.init(p.payload, n_words);
+        for (u32 k = ckpt_n(ck0); ok && k < t_local; ++k) {
+            if (pos >= total_bits) { ok = false; break; }
+            const u32 hl = decode_header(fifo.peek(pos), s);
+            pos += hl + (u64)s * p.block;
+        }
+        if (ok && pos < total_bits) {
+            const u32 hl = decode_header(fifo.peek(pos), s);
+            pos += hl + (u64)s * p.last_cnt;
+            eb = 1 + (pos >> 3);
+            if (eb > p.payload_bytes) ok = false;
+        } else {
+            ok = false;
+        }
+    }
+    if (ok) endb = eb;
+    u64 cap_pos = eb * 8;
+    u32 cap_s = 0;
+    u64 cap_c = 0;
+    spec_twalk<WARP>(p, n_segs, n_words, total_bits, ok, max_steps, next, cap_pos, cap_s, cap_c);
+    cap_state = next == SPEC_INVALID && ok && cap_pos != SPEC_INVALID ? cap_pos : SPEC_INVALID;
+    cap_sc = (u64)cap_s | (cap_c << 8);
+}
+
+// T from bit `pos` (carried width s, c headers of the frame behind it) until it meets G -> next = G's number of the
+// frame's last header.  Out of steps: (pos, s, c) say where to go on; pos = SPEC_INVALID: T cannot meet G at all.
+template <bool WARP>
+TRPX_DEVICE void spec_twalk(const DecParams& p, u64 n_segs, u64 n_words, u64 total_bits, bool ok, u64 max_steps, u64& next, u64& pos_io,
+                            u32& s_io, u64& c_io)
+{
+    const u64 seg_bits = (u64)p.seg_bytes * 8;
+    const u32 subs = p.subs_per_seg, sh = p.sub_shift;
+    const u64* q64 = (const u64*)p.payload;
+    const u64 n_q = (n_words + 1) >> 1;
+    const u64 n_ck = n_segs * subs;
+    // ---- This loop is what a batch costs, so it is kept lean:
+    // positions relative to `base` in 32 bits, the stream in four 64-bit registers (three of them read ahead), a
+    // branch-free header decode, and G consulted only where T enters a new sub-segment (its checkpoint names the
+    // first header there; the checkpoint after it is read ahead too).
+    const u64 start = ok ? pos_io : 0;
+    const u64 base = start & ~255ull;                        // a multiple of 64 and of every checkpoint spacing
+    const u64 bw = base >> 6;
+    const u64 c_lim = p.nblocks - 1;
+    u32 rel = (u32)(start - base), wrel = rel >> 6;
+    u64 w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+    u64 j2 = 0, seg_first = 0;
+    if (ok) {
+        w0 = bw + wrel < n_q ? q64[bw + wrel] : 0ull;
+        w1 = bw + wrel + 1 < n_q ? q64[bw + wrel + 1] : 0ull;
+        w2 = bw + wrel + 2 < n_q ? q64[bw + wrel + 2] : 0ull;
+        w3 = bw + wrel + 3 < n_q ? q64[bw + wrel + 3] : 0ull;
+        j2 = start / seg_bits;
+        seg_first = j2 * seg_bits;
+    }
+    // at or beyond next_chk, the next header is the first of its sub-segment (or not, where a walk resumes: then the
+    // comparison with that sub-segment's checkpoint just fails)
+    u32 next_chk = 0;
+    u64 q_pref = ~0ull, ck_pref = 0;
+    u32 s = s_io;
+    u64 c = c_io;
+    bool active = ok;
+    bool dead = false;
+    for (u64 it = 0; it < max_steps; ++it) {
+        if (active) {
+            const u64 at = base + rel;
+            // a frame too short to meet G / the stream ends: the serial chain's business
+            if (c >= c_lim || at >= total_bits || rel >= (1u << 31)) { active = false; dead = true; }
+            const u32 shb = rel & 63;
+            const u64 w = (w0 >> shb) | ((w1 << 1) << (63 - shb));
+            if (active && rel >= next_chk) {
+                while (at >= seg_first + seg_bits) { ++j2; seg_first += seg_bits; }
+                const u64 q = at >> sh;                      // (segments are whole numbers of sub-segments)
+                next_chk = (u32)(((q + 1) << sh) - base);
+                if (q < n_ck) {
+                    const u64 ck = q == q_pref ? ck_pref : p.ckpt[q];
+                    q_pref = q + 1;
+                    ck_pref = q + 1 < n_ck ? p.ckpt[q + 1] : ~0ull;
+                    if (seg_first + ckpt_rel(ck) == at && (ckpt_s(ck) == (s & 0xff) || (w & 1) == 0)) {
+                        next = p.seg_b0[j2] + ckpt_n(ck) + (c_lim - c);
+                        active = false;
+                    }
+                }
+            }
+            if (active) {
+                u32 adv;
+                if (s == 0 && (w & 1)) {                     // one-bit headers of empty blocks: up to the next checkpoint in one step
+                    u64 run = (u64)ffs64(~w | (1ull << 63)) - 1;
+                    if (run > next_chk - rel) run = next_chk - rel;
+                    if (run > c_lim - c) run = c_lim - c;
+                    adv = (u32)run;
+                    c += run;
+                } else {
+                    u32 hl, sn;
+                    decode_header_bf((u32)w, s, hl, sn);
+                    s = sn;
+                    adv = hl + s * p.block;
+                    ++c;
+                }
+                rel += adv;
+                const u32 dw = (rel >> 6) - wrel;
+                if (dw == 1) {
+                    w0 = w1; w1 = w2; w2 = w3;
+                    w3 = bw + wrel + 4 < n_q ? q64[bw + wrel + 4] : 0ull;
+                    wrel += 1;
+                } else if (dw) {
+                    wrel += dw;
+                    const u64 a0 = bw + wrel;
+                    if (dw == 2) { w0 = w2; w1 = w3; }
+                    else { w0 = a0 < n_q ? q64[a0] : 0ull; w1 = a0 + 1 < n_q ? q64[a0 + 1] : 0ull; }
+                    w2 = a0 + 2 < n_q ? q64[a0 + 2] : 0ull;
+                    w3 = a0 + 3 < n_q ? q64[a0 + 3] : 0ull;
+                }
+            }
+        }
+        if (WARP ? ballot(active) == 0u : !active) break;
+    }
+    pos_io = active && !dead ? base + rel : SPEC_INVALID;
+    s_io = s;
+    c_io = c;
+}
+
+template <int NT>
+TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 2) prolix_frame_spec_kernel(DecParams p, u64* frame_ends_out, u64* spec, u32 B, u32 R0, u32 RS, u32 max_steps)
+{
+    const u32 t = tid();
+    const u64 gthreads = (u64)nblocks() * NT, gtid = (u64)bid() * NT + t;
+    const u64 n_words = (p.payload_bytes + 3) >> 2;
+    const u64 total_bits = p.payload_bytes * 8;
+    const u64 n_segs = p.seg_base[1];                       // G: one "frame" = the whole payload
+    const u64 total_blocks = n_segs ? p.seg_b0[n_segs - 1] + p.seg_count[n_segs - 1] : 0;
+    u64* tab = spec + SPEC_HDR_WORDS;
+    TRPX_SHARED u32 win_off[SPEC_B + 1];                    // first table entry of window k
+    TRPX_SHARED u32 win_r[SPEC_B];
+    TRPX_SHARED u32 follow_idx[SPEC_B];                     // table entry the chain went through, per frame of the batch
+    TRPX_SHARED u32 follow_done;
+    if (t == 0) {
+        u32 o = 0;
+        for (u32 k = 0; k < B; ++k) { win_off[k] = o; win_r[k] = spec_radius(k, R0, RS); o += 2 * win_r[k] + 1; }
+        win_off[B] = o;
+    }
+    sync_block();
+    if (gtid == 0) {
+        // frame 0: T from bit 0 IS G, so the frame's last header is G's header nblocks - 1
+        st_relaxed(spec + 0, 0ull);
+        st_relaxed(spec + 1, p.nblocks - 1);
+        st_relaxed(spec + 2, SPEC_INVALID);
+        st_relaxed(spec + 3, 0ull);
+        st_relaxed(spec + 4, (n_segs == 0 || p.nblocks < 2) ? 1ull : 0ull);
+        st_relaxed(spec + 5, p.nblocks);
+    }
+    grid_sync();
+#ifdef TRPX_SPEC_DEBUG
+    u64 dbg_batches = 0, dbg_retries = 0, dbg_eval = 0, dbg_follow = 0, dbg_sync = 0, dbg_t0 = 0;
+#endif
+    for (;;) {
+#ifdef TRPX_SPEC_DEBUG
+        dbg_t0 = clock64();
+#endif
+        const u64 f = ld_relaxed(spec + 0), a = ld_relaxed(spec + 1), j_last = ld_relaxed(spec + 2), spf = ld_relaxed(spec + 3);
+        const u64 stride = ld_relaxed(spec + 5);             // headers of G per frame, as the last batches saw it (>= nblocks)
+        if (f >= p.n_frames || ld_relaxed(spec + 4)) break;
+        const u32 kmax = p.n_frames - f < B ? (u32)(p.n_frames - f) : B;
+        const u64 total = win_off[kmax];
+        for (u64 i0 = (u64)bid() * NT + (t & ~31u); i0 < total; i0 += gthreads) {     // (whole warps: see spec_eval)
+            const u64 i = i0 + (t & 31);
+            const bool in_table = i < total;
+            u32 klo = 0, khi = kmax;                         // window k holds entry i
+            while (khi - klo > 1) {
+                const u32 mid = (klo + khi) >> 1;
+                if (win_off[mid] <= i) klo = mid; else khi = mid;
+            }
+            const u32 k = klo, r = win_r[k];
+            const u64 centre = a + (u64)k * stride;
+            const u64 d = i - win_off[k];                    // 0 .. 2 r
+            u64 next, endb, jb, cap_pos, cap_sc;
+            const bool valid = in_table && centre + d >= r;
+            const u64 b = valid ? centre + d - r : 0;
+            u64 hint;
+            if (j_last != SPEC_INVALID) hint = j_last + (u64)(k + 1) * spf;
+            else hint = total_blocks ? (u64)((double)b / (double)total_blocks * (double)n_segs) : 0;
+            spec_eval<true>(p, n_segs, n_words, total_bits, total_blocks, valid, b, hint, max_steps, next, endb, jb, cap_pos, cap_sc);
+            if (in_table) {
+                u64* en = tab + SPEC_ENTRY_WORDS * i;
+                en[0] = next;
+                en[1] = endb;
+                en[2] = jb;
+                en[3] = cap_pos;
+                en[4] = cap_sc;
+            }
+        }
+#ifdef TRPX_SPEC_DEBUG
+        if (gtid == 0) { dbg_eval += clock64() - dbg_t0; dbg_t0 = clock64(); }
+#endif
+        grid_sync();
+#ifdef TRPX_SPEC_DEBUG
+        if (gtid == 0) { dbg_sync += clock64() - dbg_t0; dbg_t0 = clock64(); ++dbg_batches; }
+#endif
+        if (bid() == 0) {
+            // one thread follows e -> F(e) through the windows (one dependent load per frame); the frame ends are
+            // then gathered by the CTA's threads in parallel
+            if (t == 0) {
+                u64 e = a, done = 0, stop = 0;
+                for (u32 k = 0; k < kmax; ++k) {
+                    const u32 r = win_r[k];
+                    const u64 centre = a + (u64)k * stride;
+#ifdef TRPX_EMU
+                    if ((e + r < centre || e > centre + r) && getenv("EMU_TRACE_SPEC")) fprintf(stderr, "[spec]   miss at k=%u: e=%llu centre=%llu r=%u nblocks=%llu\n", k, (unsigned long long)e, (unsigned long long)centre, r, (unsigned long long)p.nblocks);
+#endif
+                    if (e + r < centre || e > centre + r) break;        // outside this batch's window: next batch
+                    const u32 i = win_off[k] + (u32)(e + r - centre);
+                    const u64* en = tab + SPEC_ENTRY_WORDS * (u64)i;
+                    u64 next = ld_relaxed(en);
+                    if (next == SPEC_INVALID) {
+                        if (ld_relaxed(en + 1) == SPEC_INVALID) { stop = 1; break; }     // not even this frame's end
+                        u64 pos = ld_relaxed(en + 3);
+                        if (f + k + 1 < p.n_frames && pos != SPEC_INVALID) {            // T ran out of steps: walk it out here, from where it stopped
+                            const u64 sc = ld_relaxed(en + 4);
+                            u32 s_t = (u32)(sc & 0xff);
+                            u64 c_t = sc >> 8;
+#ifdef TRPX_SPEC_DEBUG
+                            ++dbg_retries;
+#endif
+                            spec_twalk<false>(p, n_segs, n_words, total_bits, true, ~0ull, next, pos, s_t, c_t);
+                        }
+                    }
+                    follow_idx[k] = i;
+                    done = k + 1;
+                    if (next == SPEC_INVALID) { stop = f + done < p.n_frames ? 1 : 0; break; }
+                    e = next;
+                }
+                follow_done = (u32)done;
+                const u64 j_first = done ? ld_relaxed(tab + SPEC_ENTRY_WORDS * (u64)follow_idx[0] + 2) : 0;
+                const u64 j_now = done ? ld_relaxed(tab + SPEC_ENTRY_WORDS * (u64)follow_idx[done - 1] + 2) : j_last;
+#ifdef TRPX_EMU
+                emu_spec_followed() += done;
+                if (getenv("EMU_TRACE_SPEC")) fprintf(stderr, "[spec] batch at frame %llu: %llu of %u followed%s\n", (unsigned long long)f, (unsigned long long)done, kmax, stop ? ", stop" : "");
+#endif
+                st_relaxed(spec + 0, f + done);
+                st_relaxed(spec + 1, e);
+                st_relaxed(spec + 2, j_now);
+                st_relaxed(spec + 3, done > 1 ? (j_now - j_first) / (done - 1) : spf);
+                if (done >= 2 && !stop && e > a) {           // e - a headers of G over `done` frames
+                    const u64 seen = (e - a + done / 2) / done;
+                    st_relaxed(spec + 5, done >= 8 ? seen : (stride + seen) / 2);
+                }
+                st_relaxed(spec + 4, stop);
+#ifdef TRPX_SPEC_DEBUG
+                dbg_follow += clock64() - dbg_t0;
+#endif
+            }
+            sync_block();
+            for (u32 k = t; k < follow_done; k += NT) frame_ends_out[f + k] = ld_relaxed(tab + SPEC_ENTRY_WORDS * (u64)follow_idx[k] + 1);
+            sync_block();
+        }
+        grid_sync();
+    }
+#ifdef TRPX_SPEC_DEBUG
+    if (gtid == 0)
+        printf("[spec] frames %llu of %llu, batches %llu, retries %llu; thread 0 cycles: eval %llu, waiting at the barrier %llu, follow %llu\n",
+               (unsigned long long)ld_relaxed(spec + 0), (unsigned long long)p.n_frames, (unsigned long long)dbg_batches, (unsigned long long)dbg_retries,
+               (unsigned long long)dbg_eval, (unsigned long long)dbg_sync, (unsigned long long)dbg_follow);
+#endif
 }
 
 // The chain itself is serial, but one warp walks it co-operatively: the stream is staged in 16 KB

@@ -9,6 +9,7 @@
 // arithmetic against the oracle without a GPU; it is never linked into libtrpx_b200.so and is not a
 // fallback: the product library has no host execution path.
 #pragma once
+#include <tuple>
 
 #include <stddef.h>
 #include <stdint.h>
@@ -318,10 +319,13 @@ inline cudaError_t launch(void (*kern)(KArgs...), u32 grid, u32 block, size_t sm
 
 // grid-wide barrier of a cooperative launch (all CTAs resident by construction)
 TRPX_DEVICE void grid_sync() { cooperative_groups::this_grid().sync(); }
-template <typename P>
-inline cudaError_t launch_coop(void (*kern)(P), u32 grid, u32 block, size_t smem, cudaStream_t st, P arg)
+template <typename... P, typename... A>
+inline cudaError_t launch_coop(void (*kern)(P...), u32 grid, u32 block, size_t smem, cudaStream_t st, A... args)
 {
-    void* kargs[] = {(void*)&arg};
+    std::tuple<P...> held{static_cast<P>(args)...};          // the launch reads the arguments through pointers
+    void* kargs[sizeof...(P)];
+    size_t n = 0;
+    std::apply([&](auto&... a) { ((kargs[n++] = (void*)&a), ...); }, held);
     return cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(block), kargs, smem, st);
 }
 
@@ -476,10 +480,10 @@ inline cudaError_t launch(void (*kern)(KArgs...), u32 grid, u32 block, size_t sm
 }
 // the emulator runs the blocks of a grid one after another, so a "cooperative" launch is one CTA
 inline void grid_sync() { ::emu::sync_block(); }
-template <typename P>
-inline cudaError_t launch_coop(void (*kern)(P), u32, u32 block, size_t smem, cudaStream_t, P arg)
+template <typename... P, typename... A>
+inline cudaError_t launch_coop(void (*kern)(P...), u32, u32 block, size_t smem, cudaStream_t, A... args)
 {
-    ::emu::run_grid(1, block, smem, [&]() { kern(arg); });
+    ::emu::run_grid(1, block, smem, [&]() { kern(static_cast<P>(args)...); });
     return cudaSuccess;
 }
 #endif
