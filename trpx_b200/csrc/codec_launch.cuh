@@ -259,6 +259,17 @@ inline DecPlan dec_plan(int out_dtype, u64 payload_bytes, u64 n_values, u64 n_fr
 inline u32 g_spec_params[4] = {SPEC_B, SPEC_R0, SPEC_RS, SPEC_MAX_STEPS};   // .. and T steps per candidate
 constexpr u64 SPEC_MIN_FRAMES = 4, SPEC_MIN_BLOCKS = 64;
 
+// CTAs of the cooperative resolve kernel: a warp puts its segments right one after another, so a small call wants
+// few segments per warp (four), but no more CTAs than that takes -- the grid barriers cost by the CTA; one CTA scans
+// one frame at the end.
+inline u32 resolve_grid(const DecPlan& pl, u64 n_frames, u32 coop_grid)
+{
+    u64 g = div_up(pl.max_segs, (u64)(RESOLVE_NT / 32) * 4);
+    if (g < n_frames) g = n_frames;
+    if (g > coop_grid) g = coop_grid;
+    return g ? (u32)g : 1u;
+}
+
 // Frame sizes unknown: the recovery pass (find_frames_async) first uses the scratch for the tables of the G plan --
 // the payload as one frame, checkpoints forced -- and the recovered frame ends sit behind BOTH layouts.
 inline DecPlan dec_plan_chain(const DecPlan& pl, int out_dtype, u64 payload_bytes, u32 block)
@@ -369,7 +380,7 @@ inline void find_frames_async(Launcher& L, const void* d_payload, u64 payload_by
     L.err = launch(prolix_walk_kernel<WALK_NT>, walk_grid, (u32)WALK_NT, walk_smem, L.stream, p);
     L.count("prolix_walk");
     if (L.err != cudaSuccess) return;
-    L.err = launch_coop(prolix_resolve_kernel<RESOLVE_NT>, coop_grid, (u32)RESOLVE_NT, 0, L.stream, p);
+    L.err = launch_coop(prolix_resolve_kernel<RESOLVE_NT>, resolve_grid(gpl, 1, coop_grid), (u32)RESOLVE_NT, 0, L.stream, p);
     L.count("prolix_resolve");
     if (L.err != cudaSuccess) return;
     // T: follow the frames -- speculatively in parallel, then serially whatever that pass left
@@ -458,7 +469,7 @@ inline void decode_async(Launcher& L, const void* d_payload, u64 payload_bytes, 
     L.err = launch(prolix_walk_kernel<WALK_NT>, walk_grid, (u32)WALK_NT, walk_smem, L.stream, p);
     L.count("prolix_walk");
     if (L.err != cudaSuccess) return;
-    L.err = launch_coop(prolix_resolve_kernel<RESOLVE_NT>, coop_grid, (u32)RESOLVE_NT, 0, L.stream, p);
+    L.err = launch_coop(prolix_resolve_kernel<RESOLVE_NT>, resolve_grid(pl, n_frames, coop_grid), (u32)RESOLVE_NT, 0, L.stream, p);
     L.count("prolix_resolve");
     if (L.err != cudaSuccess) return;
     if (!pl.staged) {

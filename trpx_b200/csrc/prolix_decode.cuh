@@ -741,6 +741,12 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_resolve_kernel(DecParams p)
     const u64 n_segs = p.seg_base[p.n_frames];
     const u64 n_words = (p.payload_bytes + 3) >> 2;
     const u64 gthreads = (u64)nblocks() * NT, gtid = (u64)bid() * NT + t;
+    const u64 gwarps = gthreads / 32, gwarp = gtid / 32;
+    u32 per_warp = 32;
+    if (n_segs < gthreads) {
+        per_warp = (u32)((n_segs + gwarps - 1) / gwarps);
+        if (per_warp < 1) per_warp = 1;
+    }
     NoSink ns;
     ChainWin win;
     win.chunk = sm_win[warp];
@@ -752,13 +758,14 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_resolve_kernel(DecParams p)
         // or raises until every CTA has passed this sweep's grid barrier
         u32* flag = &p.changed[sweep % 3];
         if (gtid == 0) p.changed[(sweep + 1) % 3] = 0;
-        // a warp checks 32 consecutive segments at a time (one per lane) and then puts the wrong ones right ONE BY ONE,
-        // all lanes together (rewalk_until_merged_warp)
-        for (u64 base = (gtid - lane); base < n_segs; base += gthreads) {
+        // a warp checks `per_warp` consecutive segments at a time (one per lane: 32, fewer when the call has fewer
+        // segments than the grid has lanes) and then puts the wrong ones right ONE BY ONE, all lanes together
+        // (rewalk_until_merged_warp) -- so a small call spreads its fix-ups over as many warps as it can
+        for (u64 base = gwarp * per_warp; base < n_segs; base += gwarps * per_warp) {
             const u64 jl = base + lane;
             bool fix = false;
             u64 want = 0;
-            if (jl < n_segs) {
+            if (lane < per_warp && jl < n_segs) {
                 const SegInfo gl = seg_info(p, jl);
                 if (gl.idx != 0) {
                     want = ld_relaxed(&p.seg_exit[jl - 1]);
