@@ -8,7 +8,7 @@ d = defaultdict(list)
 for r in rows[1:]:
     v = float(r[vi].replace(',', ''))
     d[r[ki][:90]].append(v * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(r[ui], 1.0))
-ours = {k: v for k, v in d.items() if "trpx::" in k}
+ours = {k: v for k, v in d.items() if any(t in k for t in ("terse_", "prolix_", "publish"))}
 tot = sum(sum(v) for v in ours.values())
 print("kernels of libtrpx_b200.so (share = of their sum; cold-cache, serialised under ncu)")
 for k, v in sorted(ours.items(), key=lambda kv: -sum(kv[1])):
