@@ -318,7 +318,13 @@ inline cudaError_t launch(void (*kern)(KArgs...), u32 grid, u32 block, size_t sm
 }
 
 // grid-wide barrier of a cooperative launch (all CTAs resident by construction)
-TRPX_DEVICE void grid_sync() { cooperative_groups::this_grid().sync(); }
+// (cooperative_groups aborts -- a trap -- when the grid was not launched cooperatively; launch_coop is the only way these
+// kernels are launched, and checking validity here lets the compiler drop that path: no kernel of this library can trap)
+TRPX_DEVICE void grid_sync()
+{
+    const cooperative_groups::grid_group g = cooperative_groups::this_grid();
+    if (g.is_valid()) g.sync();
+}
 template <typename... P, typename... A>
 inline cudaError_t launch_coop(void (*kern)(P...), u32 grid, u32 block, size_t smem, cudaStream_t st, A... args)
 {
