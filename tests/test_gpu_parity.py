@@ -117,6 +117,35 @@ def test_foreign_stack_frame_sizes_are_recovered_from_the_stream(codec):
     assert np.array_equal(d, st[40:43])
 
 
+def test_foreign_stack_many_frames_mixed_content(codec):
+    """Several batches of the speculative frame chain (64 frames each), with what makes its windows miss or its candidates
+    give up: empty frames, frames of constant width (T and G never re-synchronise: the serial chain takes over), dense and
+    sparse frames side by side, a ragged last block.  The recovered sizes must be the encoder's, frame by frame."""
+    rng = np.random.default_rng(5)
+    n = 128 * 130 + 5
+    frames = []
+    for f in range(330):
+        kind = f % 11
+        if kind == 3:
+            a = np.zeros(n, np.uint16)
+        elif kind == 7:
+            a = rng.integers(0, 4, n).astype(np.uint16)
+            a[::12] = 3                                            # every block 2 bits wide: nothing but "same width" headers
+        elif kind == 9:
+            a = (rng.random(n) < 0.002).astype(np.uint16) * 9     # sparse
+        else:
+            a = rng.poisson(2.0 + (f % 5), n).astype(np.uint16)
+        frames.append(a)
+    st = np.stack(frames)
+    p, fb, pb = codec.encode(st)
+    d, fb2 = codec.decode(p, n, st.shape[0], False, np.uint16)
+    assert np.array_equal(fb2, fb)
+    assert np.array_equal(d, st)
+    with pytest.raises(trpx_b200.TrpxError) as e:                  # the stream ends inside frame 200: flagged, no hang
+        codec.decode(p[:int(fb[:200].sum()) + 7], n, st.shape[0], False, np.uint16)
+    assert e.value.status == trpx_b200.ERR_MALFORMED
+
+
 def test_signed_dark_subtracted_frames(codec):
     for dt in (orc.I16, orc.I32):
         st = np.stack([orc.synth_frame(dt, 512, 512, 3.0, 0, 77 + f) for f in range(6)])
