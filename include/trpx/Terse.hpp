@@ -31,11 +31,14 @@
 #include <iterator>
 #include <limits>
 #include <memory>
+#include <new>
 #include <ostream>
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "../trpx_b200.h"
@@ -117,6 +120,37 @@ inline std::uint8_t* pinned_scratch(std::size_t bytes)
         h.cap = h.p ? bytes + bytes / 8 : 0;
     }
     return static_cast<std::uint8_t*>(h.p);
+}
+
+// The payload lives in a byte vector that is NOT value-initialised when it grows: first-touching fresh pages by zero-
+// filling them and then overwriting them costs more than the whole GPU encode (measured: 226 MB appended in 98 ms by
+// one thread, page faults included, against 43 ms for encoding the 1 GB of pixels behind them).
+template <typename T>
+struct default_init_allocator : std::allocator<T> {
+    template <typename U> struct rebind { using other = default_init_allocator<U>; };
+    using std::allocator<T>::allocator;
+    template <typename U> void construct(U* p) noexcept(std::is_nothrow_default_constructible_v<U>) { ::new (static_cast<void*>(p)) U; }
+    template <typename U, typename... A> void construct(U* p, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A>(a)...); }
+};
+using byte_vector = std::vector<std::uint8_t, default_init_allocator<std::uint8_t>>;
+
+// dst += [src, src + n): large appends are copied (and their fresh pages faulted in) by a few threads side by side
+inline void append_bytes(byte_vector& dst, const std::uint8_t* src, std::size_t n)
+{
+    const std::size_t old = dst.size();
+    dst.resize(old + n);
+    std::uint8_t* d = dst.data() + old;
+    constexpr std::size_t PER_THREAD = std::size_t(16) << 20;
+    std::size_t threads = n / PER_THREAD;
+    if (threads > 6) threads = 6;
+    if (threads < 2) { std::memcpy(d, src, n); return; }
+    std::vector<std::thread> th;
+    const std::size_t step = ((n + threads - 1) / threads + 4095) & ~std::size_t(4095);
+    for (std::size_t t = 0; t < threads; ++t) {
+        const std::size_t lo = t * step, hi = lo + step < n ? lo + step : n;
+        if (lo < hi) th.emplace_back([=] { std::memcpy(d + lo, src + lo, hi - lo); });
+    }
+    for (auto& x : th) x.join();
 }
 
 inline void check(int status, trpx_ctx* ctx)
@@ -372,7 +406,7 @@ private:
     std::size_t d_size = 0;
     unsigned d_prolix_bits = 0;
     std::vector<std::size_t> d_dim;
-    std::vector<std::uint8_t> d_terse_data;
+    trpx_detail::byte_vector d_terse_data;
     std::vector<std::size_t> d_frame_bytes;         // payload bytes of each frame; 0 = not known yet (read from a file)
 
     template <typename Iterator>
@@ -410,7 +444,7 @@ private:
         }
         if (multi && rc != TRPX_OK) throw std::runtime_error(std::string("trpx_b200: ") + trpx_strerror(rc) + " (" + trpx_pool_last_error(trpx_detail::pool()) + ")");
         trpx_detail::check(rc, ctx);
-        d_terse_data.insert(d_terse_data.end(), scratch, scratch + total);
+        trpx_detail::append_bytes(d_terse_data, scratch, total);
         d_frame_bytes.insert(d_frame_bytes.end(), fb.begin(), fb.end());
         if (pb > d_prolix_bits) d_prolix_bits = pb;
     }
