@@ -29,6 +29,8 @@ struct DevBuf {
     size_t cap = 0;
 };
 
+constexpr int MAX_STAGE_THREADS = 8;   // helper threads that stage pageable host memory (two pinned 8 MB slots each)
+
 struct Lane {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // host flavours: payload D2H of the encoder, off the lane's main stream
@@ -96,9 +98,12 @@ struct trpx_ctx {
     // staging of PAGEABLE caller memory (host flavours): helper threads copy chunks into pinned slots, the copy engine
     // takes them from there (the driver's own bounce path for pageable memory moved ~5 GB/s on the B200 hosts)
     uint8_t* stage_ring = nullptr;
-    cudaEvent_t stage_ev[6] = {};
-    bool stage_used[6] = {};
+    cudaEvent_t stage_ev[2 * MAX_STAGE_THREADS] = {};
+    bool stage_used[2 * MAX_STAGE_THREADS] = {};
     int stage_threads = 3;             // TRPX_STAGE_THREADS (0: leave pageable copies to the driver)
+    uint8_t* unstage_ring = nullptr;   // the same for downloads into pageable memory: pinned slots, one stream per helper
+    cudaStream_t unstage_stream[MAX_STAGE_THREADS] = {};
+    cudaEvent_t unstage_ev[2 * MAX_STAGE_THREADS] = {};
     EncProgress enc_progress;
     std::vector<u32> call_status;
     u32 coop_grid = 0;
@@ -261,7 +266,7 @@ cudaError_t h2d_async(trpx_ctx* c, void* dst, const void* src, size_t bytes, cud
     const int T = c->stage_threads;
     if (T <= 0 || bytes < 2 * STAGE_CHUNK || !is_pageable(src)) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
     if (!c->stage_ring) {
-        if (cudaHostAlloc((void**)&c->stage_ring, 6 * STAGE_CHUNK, cudaHostAllocDefault) != cudaSuccess) {
+        if (cudaHostAlloc((void**)&c->stage_ring, 2 * (size_t)MAX_STAGE_THREADS * STAGE_CHUNK, cudaHostAllocDefault) != cudaSuccess) {
             cudaGetLastError();
             c->stage_ring = nullptr;
             return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
@@ -285,6 +290,59 @@ cudaError_t h2d_async(trpx_ctx* c, void* dst, const void* src, size_t bytes, cud
                 c->stage_used[slot] = true;
                 if (e != cudaSuccess) { err[(size_t)t] = e; return; }
             }
+        });
+    for (auto& x : th) x.join();
+    for (cudaError_t e : err)
+        if (e != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+// Device -> PAGEABLE host memory, blocking: helper threads pull 8 MB chunks into pinned slots on their own streams (two
+// slots each: the DMA of a helper's next chunk runs while it copies the previous one out) and memcpy them to `dst`.
+// The driver's own path for pageable destinations does the same with ONE thread.  `ready`: the event after which `src`
+// may be read.  Falls back to a plain synchronous copy when the ring cannot be allocated.
+cudaError_t d2h_staged(trpx_ctx* c, void* dst, const void* src, size_t bytes, cudaEvent_t ready)
+{
+    const int T = c->stage_threads;
+    if (T > 0 && !c->unstage_ring) {
+        if (cudaHostAlloc((void**)&c->unstage_ring, 2 * (size_t)MAX_STAGE_THREADS * STAGE_CHUNK, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            c->unstage_ring = nullptr;
+        } else {
+            for (cudaStream_t& st : c->unstage_stream) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+            for (cudaEvent_t& e : c->unstage_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        }
+    }
+    if (T <= 0 || !c->unstage_ring) {
+        cudaError_t e = cudaEventSynchronize(ready);
+        return e != cudaSuccess ? e : cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost);
+    }
+    const size_t n_chunks = (bytes + STAGE_CHUNK - 1) / STAGE_CHUNK;
+    std::vector<cudaError_t> err((size_t)T, cudaSuccess);
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; ++t)
+        th.emplace_back([&, t] {
+            cudaSetDevice(c->device);
+            cudaStream_t st = c->unstage_stream[t];
+            cudaError_t e = cudaStreamWaitEvent(st, ready, 0);
+            auto issue = [&](size_t i, int k) {                   // chunk i -> this helper's slot k
+                const size_t off = i * STAGE_CHUNK, n = bytes - off < STAGE_CHUNK ? bytes - off : STAGE_CHUNK;
+                const int slot = t + T * k;
+                cudaError_t r = cudaMemcpyAsync(c->unstage_ring + (size_t)slot * STAGE_CHUNK, (const uint8_t*)src + off, n, cudaMemcpyDeviceToHost, st);
+                return r != cudaSuccess ? r : cudaEventRecord(c->unstage_ev[slot], st);
+            };
+            int k = 0;
+            if (e == cudaSuccess && (size_t)t < n_chunks) e = issue((size_t)t, 0);
+            for (size_t i = (size_t)t; i < n_chunks && e == cudaSuccess; i += (size_t)T, k ^= 1) {
+                if (i + (size_t)T < n_chunks) e = issue(i + (size_t)T, k ^ 1);
+                const int slot = t + T * k;
+                const cudaError_t w = cudaEventSynchronize(c->unstage_ev[slot]);
+                if (w != cudaSuccess) { e = w; break; }
+                const size_t off = i * STAGE_CHUNK, n = bytes - off < STAGE_CHUNK ? bytes - off : STAGE_CHUNK;
+                memcpy((uint8_t*)dst + off, c->unstage_ring + (size_t)slot * STAGE_CHUNK, n);
+            }
+            if (e != cudaSuccess) cudaStreamSynchronize(st);     // nothing of this call stays in flight
+            err[(size_t)t] = e;
         });
     for (auto& x : th) x.join();
     for (cudaError_t e : err)
@@ -365,8 +423,13 @@ int trpx_ctx_create(int device, trpx_ctx** out)
     c->enc_batch_bytes = getenv("TRPX_ENC_BATCH_MB") ? (size_t)env_u32("TRPX_ENC_BATCH_MB", 0) << 20 : c->batch_bytes;
     c->enc_lanes = (int)env_u32("TRPX_ENC_LANES", (u32)c->enc_lanes);
     c->dec_lanes = (int)env_u32("TRPX_DEC_LANES", (u32)c->dec_lanes);
+    {   // half the host's hardware threads, at most six: host memory saturates there (1 / 2 / 3 / 5 / 8 threads moved
+        // 1 GB into pageable memory in 141 / 81 / 63 / 53 / 52 ms on the bench host)
+        const unsigned hw = std::thread::hardware_concurrency();
+        if (hw) c->stage_threads = hw / 2 < 1 ? 1 : hw / 2 > 6 ? 6 : (int)(hw / 2);
+    }
     c->stage_threads = (int)env_u32("TRPX_STAGE_THREADS", (u32)c->stage_threads);
-    if (c->stage_threads > 3) c->stage_threads = 3;
+    if (c->stage_threads > MAX_STAGE_THREADS) c->stage_threads = MAX_STAGE_THREADS;
     if (c->enc_lanes < 1) c->enc_lanes = 1;
     if (c->enc_lanes > N_LANES) c->enc_lanes = N_LANES;
     if (c->dec_lanes < 1) c->dec_lanes = 1;
@@ -404,6 +467,13 @@ void trpx_ctx_destroy(trpx_ctx* c)
     if (c->d_call_status.p) cudaFree(c->d_call_status.p);
     if (c->d_foreign.p) cudaFree(c->d_foreign.p);
     if (c->stage_ring) cudaFreeHost(c->stage_ring);
+    if (c->unstage_ring) {
+        cudaFreeHost(c->unstage_ring);
+        for (cudaStream_t st : c->unstage_stream)
+            if (st) cudaStreamDestroy(st);
+        for (cudaEvent_t e : c->unstage_ev)
+            if (e) cudaEventDestroy(e);
+    }
     for (cudaEvent_t e : c->stage_ev)
         if (e) cudaEventDestroy(e);
     delete c;
@@ -684,6 +754,15 @@ int trpx_decode_host(trpx_ctx* c, const uint8_t* payload, size_t payload_bytes, 
     if (!ensure(c, c->d_call_status, n_batches * sizeof(u32))) return TRPX_ERR_NOMEM;
     c->call_status.assign(n_batches, 0);
     size_t issued = 0;
+    // A pageable destination is filled by helper threads (d2h_staged), one batch behind the batch being issued: the GPU
+    // works on batch b while the host drains batch b - 1, and a lane's buffer is free again as soon as its drain returns.
+    const bool staged_out = c->stage_threads > 0 && n_frames * frame_raw >= 2 * STAGE_CHUNK && is_pageable(out);
+    auto drain_staged = [&](size_t b) {
+        Lane& l = c->lanes[b % (size_t)nl];
+        const size_t nf = (b * fpb + fpb <= n_frames) ? fpb : n_frames - b * fpb;
+        if (!cuda_ok(c, d2h_staged(c, (uint8_t*)out + b * fpb * frame_raw, l.d_out.p, nf * frame_raw, l.ev_done), "D2H pixels (staged)") && rc == TRPX_OK)
+            rc = TRPX_ERR_CUDA;
+    };
 
     for (size_t b = 0; b < n_batches && rc == TRPX_OK; ++b) {
         const int li = (int)(b % nl);
@@ -720,12 +799,18 @@ int trpx_decode_host(trpx_ctx* c, const uint8_t* payload, size_t payload_bytes, 
         if (!cuda_ok(c, L.err, "decode launch")) { rc = TRPX_ERR_CUDA; break; }
         // the pixels leave on the lane's copy stream: the lane's next payload upload does not wait for them
         cudaEventRecord(l.ev_done, l.stream);
+        issued = b + 1;
+        if (staged_out) {
+            if (nl < 2) drain_staged(b);
+            else if (b >= 1) drain_staged(b - 1);
+            continue;
+        }
         cudaStreamWaitEvent(l.copy_stream, l.ev_done, 0);
         cudaMemcpyAsync((uint8_t*)out + b * fpb * frame_raw, l.d_out.p, nf * frame_raw, cudaMemcpyDeviceToHost, l.copy_stream);
         cudaEventRecord(l.ev_drained, l.copy_stream);
         l.drain_pending = true;
-        issued = b + 1;
     }
+    if (staged_out && nl >= 2 && issued >= 1 && rc == TRPX_OK) drain_staged(issued - 1);
     for (int li = 0; li < nl; ++li) {
         Lane& l = c->lanes[li];
         if (!cuda_ok(c, cudaStreamSynchronize(l.stream), "decode batch") && rc == TRPX_OK) rc = TRPX_ERR_CUDA;
