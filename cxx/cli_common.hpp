@@ -3,6 +3,7 @@
 
 #include <chrono>
 #include <filesystem>
+#include <future>
 #include <iostream>
 #include <string>
 #include <vector>
@@ -33,6 +34,22 @@ inline bool has_extension(fs::path const& p, std::initializer_list<const char*> 
     for (const char* x : exts)
         if (e == x) return true;
     return false;
+}
+
+// File I/O overlapped with the GPU: the tools spend their time reading and writing files, so
+// file k + 1 is read and parsed by a helper thread while file k is on the GPU and being written.  `load` runs on the
+// helper and must not print (messages stay in file order: it returns them); `process` runs on the calling thread, in
+// order.  At most two files are in memory at a time.
+template <typename Loaded, typename Load, typename Process>
+void for_each_prefetched(std::vector<fs::path> const& files, Load load, Process process)
+{
+    std::future<Loaded> next;
+    if (!files.empty()) next = std::async(std::launch::async, load, files[0]);
+    for (std::size_t i = 0; i < files.size(); ++i) {
+        Loaded cur = next.get();
+        if (i + 1 < files.size()) next = std::async(std::launch::async, load, files[i + 1]);
+        process(files[i], cur);
+    }
 }
 
 struct Report {

@@ -2,13 +2,15 @@
 // (src/prolix.cpp:18-128): every *.trpx argument becomes a .tif next to it and the .trpx is deleted; output type
 // int16 / uint16 for <= 16 bits per value, int32 / uint32 up to 32 (src/prolix.cpp:69-97; the reference's 17..32-bit
 // branches decode through 16-bit views -- SURVEY App. C6 -- here they use the 32-bit type); square images are assumed
-// when the header holds no dimensions (:61-65).  All frames of a file are decoded in ONE call (Terse::prolix_frames).
+// when the header holds no dimensions (:61-65).  All frames of a file are decoded in ONE call (Terse::prolix_frames), and
+// the next file is read while the current one is expanded and written (cli_common.hpp: for_each_prefetched).
 #include <array>
 #include <chrono>
 #include <cmath>
 #include <filesystem>
 #include <fstream>
 #include <iostream>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -42,16 +44,37 @@ int main(int argc, char const* argv[])
         return 0;
     }
     Report rep;
-    for (fs::path const& source : args.files) {
-        if (!fs::is_regular_file(source) || !has_extension(source, {".trpx"})) continue;
+    std::vector<fs::path> todo;
+    for (fs::path const& source : args.files)
+        if (fs::is_regular_file(source) && has_extension(source, {".trpx"})) todo.push_back(source);
+    struct Loaded {
+        bool opened = false;
+        std::unique_ptr<jpa::Terse> packed;
+        std::string error;
+        Seconds io{0};
+    };
+    auto load = [](fs::path const& source) {                           // (helper thread: reads the container, never prints)
+        Loaded l;
         const auto t_open = Clock::now();
         try {
             std::ifstream in(source, std::ios::binary);
-            if (!in.is_open()) { std::cerr << "Failed to open input file " << source << std::endl; continue; }
-            jpa::Terse packed(in);
-            in.close();
+            l.opened = in.is_open();
+            if (l.opened) l.packed = std::make_unique<jpa::Terse>(in);
+        } catch (std::exception const& e) {
+            l.error = e.what();
+        }
+        l.io = Clock::now() - t_open;
+        return l;
+    };
+    bool give_up = false;
+    for_each_prefetched<Loaded>(todo, load, [&](fs::path const& source, Loaded& got) {
+        if (give_up) return;
+        try {
+            if (!got.opened) { std::cerr << "Failed to open input file " << source << std::endl; return; }
+            if (!got.error.empty()) throw std::runtime_error(got.error);
+            jpa::Terse& packed = *got.packed;
             const auto t_gpu = Clock::now();
-            rep.io += t_gpu - t_open;
+            rep.io += got.io;
             std::size_t w, h;                                          // no dimensions in the header: a square image
             if (packed.dim().size() < 2) w = h = std::size_t(std::sqrt(double(packed.size())));
             else { w = packed.dim()[0]; h = packed.dim()[1]; }
@@ -64,7 +87,8 @@ int main(int argc, char const* argv[])
             if (bits > 32) {
                 std::cerr << "Terse file " << source << " encodes data that requires 64 bits per pixel." << std::endl;
                 std::cerr << "Prolix cannot process such trpx-stacks." << std::endl;
-                return 0;
+                give_up = true;                                        // (the reference returns here, src/prolix.cpp:93-97)
+                return;
             }
             if (packed.is_signed()) stack = bits <= 16 ? expand<std::int16_t>(packed, w, h, Kind::Int) : expand<std::int32_t>(packed, w, h, Kind::Int);
             else stack = bits <= 16 ? expand<std::uint16_t>(packed, w, h, Kind::Uint) : expand<std::uint32_t>(packed, w, h, Kind::Uint);
@@ -96,7 +120,8 @@ int main(int argc, char const* argv[])
         } catch (std::exception const& e) {
             std::cerr << "Error processing " << source << ": " << e.what() << std::endl;
         }
-    }
+    });
+    if (give_up) return 0;
     if (args.verbose) rep.print("Expanded", "Prolix expanded : ", args);
     return 0;
 }

@@ -1,7 +1,8 @@
 // terse -- compress TIFF stacks to .trpx on the GPU.  Same command line and file semantics as the reference CLI
 // (src/terse.cpp:20-104): every *.tif / *.tiff argument becomes a .trpx next to it and the TIFF is deleted;
 // -help, -verbose ("Terse compressed", "User time", "IO time", "Compression rate").  The whole stack of a file goes
-// to the GPU in ONE call (Terse::push_back_frames) instead of one push_back per image.
+// to the GPU in ONE call (Terse::push_back_frames) instead of one push_back per image, and the next file is read while
+// the current one is compressed and written (cli_common.hpp: for_each_prefetched).
 #include <chrono>
 #include <cmath>
 #include <filesystem>
@@ -48,14 +49,33 @@ int main(int argc, char const* argv[])
     }
     Report rep;
     double trpx_bytes = 0, tiff_bytes = 0;
-    for (fs::path const& tif : args.files) {
-        if (!fs::is_regular_file(tif) || !has_extension(tif, {".tiff", ".tif", ".TIFF", ".TIF"})) continue;
+    std::vector<fs::path> todo;
+    for (fs::path const& tif : args.files)
+        if (fs::is_regular_file(tif) && has_extension(tif, {".tiff", ".tif", ".TIFF", ".TIF"})) todo.push_back(tif);
+    struct Loaded {
+        bool opened = false;
+        std::vector<jpa::tiffio::Image> stack;
+        std::string error;
+        Seconds io{0};
+    };
+    auto load = [](fs::path const& tif) {                              // (helper thread: reads and parses, never prints)
+        Loaded l;
+        const auto t_open = Clock::now();
         try {
-            const auto t_open = Clock::now();
             std::ifstream in(tif, std::ios::binary);
-            if (!in.is_open()) { std::cerr << "Failed to open input file " << tif << std::endl; continue; }
-            const std::vector<jpa::tiffio::Image> stack = jpa::tiffio::read(in);
-            in.close();
+            l.opened = in.is_open();
+            if (l.opened) l.stack = jpa::tiffio::read(in);
+        } catch (std::exception const& e) {
+            l.error = e.what();
+        }
+        l.io = Clock::now() - t_open;
+        return l;
+    };
+    for_each_prefetched<Loaded>(todo, load, [&](fs::path const& tif, Loaded& got) {
+        try {
+            if (!got.opened) { std::cerr << "Failed to open input file " << tif << std::endl; return; }
+            if (!got.error.empty()) throw std::runtime_error(got.error);
+            std::vector<jpa::tiffio::Image> const& stack = got.stack;
             if (stack.empty()) throw std::runtime_error("TIFF file contains no image.");
             jpa::tiffio::Image const& first = stack.front();
             for (auto const& im : stack) {
@@ -102,11 +122,11 @@ int main(int argc, char const* argv[])
             fs::remove(tif);
             ++rep.done;
             rep.user += Clock::now() - t_gpu;
-            rep.io += t_gpu - t_open;
+            rep.io += got.io;
         } catch (std::exception const& e) {
             std::cerr << "Error processing " << tif << ": " << e.what() << std::endl;
         }
-    }
+    });
     if (args.verbose) {
         rep.print("Compressed", "Terse compressed: ", args);
         if (tiff_bytes > 0) std::cout << "Compression rate: " << std::round(1000 * (1 - trpx_bytes / tiff_bytes)) / 10 << "%\n";
