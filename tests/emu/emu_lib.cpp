@@ -17,13 +17,17 @@ int emu_encode(const void* px, int dtype, size_t n, size_t frames, unsigned bloc
     EncPlan pl = enc_plan(dtype, px, n, frames, block);
     if (!pl.ok) return 1;
     if (used_fast) *used_fast = pl.fast ? 1 : 0;
-    void* scratch = malloc(pl.scratch_bytes);
-    memset(scratch, 0x5A, pl.scratch_bytes);
+    const size_t guard = 4096;                               // nothing may be written past the plan's scratch size
+    unsigned char* scratch = (unsigned char*)malloc(pl.scratch_bytes + guard);
+    memset(scratch, 0x5A, pl.scratch_bytes + guard);
     Launcher L{nullptr, getenv("EMU_SMS") ? (u32)atoi(getenv("EMU_SMS")) : 1u, nullptr, cudaSuccess};
     encode_async(L, dtype, px, n, frames, block, out, cap, (u64*)frame_ends, prolix_bits, status, scratch, pl,
                  3, dbg_incl_stride);
+    int rc = 0;
+    for (size_t i = 0; i < guard; ++i)
+        if (scratch[pl.scratch_bytes + i] != 0x5A) rc = 3;
     free(scratch);
-    return 0;
+    return rc;
 }
 
 }
@@ -37,13 +41,17 @@ extern "C" int emu_decode(const uint8_t* payload, size_t payload_bytes, int is_s
     if (!pl.ok) return 1;
     if (used_staged) *used_staged = pl.staged ? 1 : 0;
     const size_t need = (dec_scratch_need(pl, out_dtype, payload_bytes, block, frames, frame_ends == nullptr) + 255) / 256 * 256;
-    void* scratch = aligned_alloc(256, need);
-    memset(scratch, 0x5A, need);
+    const size_t guard = 4096;                               // nothing may be written past what dec_scratch_need() asked for
+    unsigned char* scratch = (unsigned char*)aligned_alloc(256, need + guard);
+    memset(scratch, 0x5A, need + guard);
     Launcher L{nullptr, 1, nullptr, cudaSuccess};
     decode_async(L, payload, payload_bytes, is_signed != 0, block, n, frames, (const u64*)frame_ends,
                  (u64*)frame_ends_out, out, out_dtype, status, scratch, pl, 1);
+    int rc = 0;
+    for (size_t i = 0; i < guard; ++i)
+        if (scratch[need + i] != 0x5A) rc = 3;
     free(scratch);
-    return 0;
+    return rc;
 }
 
 // batch geometry of the speculative frame chain (tests shrink it to exercise window misses)
