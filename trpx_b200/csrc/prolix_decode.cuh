@@ -506,13 +506,30 @@ TRPX_KERNEL void TRPX_LAUNCH_BOUNDS(NT, 1) prolix_segments_kernel(DecParams p)
         if ((u32)i < warp) base += v;
         total += v;
     }
-    // every CTA of the grid repeats the (cheap) scan; the table entries are shared out frame by frame
+    // every CTA of the grid repeats the (cheap) scan; the table entries are shared out frame by frame.  A frame's
+    // entries are written by the whole warp (the lanes serve each other's frames in turn): a stack of a few large
+    // frames -- or the one "frame" of the G plan -- is thousands of entries behind a single thread otherwise.
     u64 run = base + incl - mine;
-    for (u64 f = f0; f < f1; ++f) {
-        const u64 nseg = nseg_of(f);
-        if (f % nblocks() == bid()) {
-            p.seg_base[f] = run;
-            for (u64 i = 0; i < nseg && run + i < p.max_segs; ++i) p.seg_frame[run + i] = (u32)f;
+    const u64 cnt_mine = f1 > f0 ? f1 - f0 : 0;
+    u32 cnt_max = (u32)(cnt_mine < 0xffffffffull ? cnt_mine : 0xffffffffull);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        const u32 v = shfl_xor(cnt_max, d);
+        cnt_max = v > cnt_max ? v : cnt_max;
+    }
+    for (u32 k = 0; k < cnt_max; ++k) {
+        const bool have = k < cnt_mine;
+        const u64 f = f0 + k;
+        const u64 nseg = have ? nseg_of(f) : 0;
+        const bool write = have && f % nblocks() == bid();
+        if (write) p.seg_base[f] = run;
+        u32 todo = ballot(write && nseg != 0);
+        while (todo) {
+            const int l = ffs32(todo) - 1;
+            todo &= todo - 1;
+            const u64 r = shfl(run, l), n = shfl(nseg, l);
+            const u32 ff = shfl((u32)f, l);
+            for (u64 i = lane; i < n && r + i < p.max_segs; i += 32) p.seg_frame[r + i] = ff;
         }
         run += nseg;
     }
